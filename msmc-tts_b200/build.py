@@ -1,0 +1,59 @@
+"""Build the sm_100a C-ABI library of the MSMC-VQ-GAN hot path, in-tree.
+
+    python msmc-tts_b200/build.py            # -> msmc-tts_b200/msmctts/_b200/libmsmc_b200.so
+
+nvcc cross-compiles without a GPU.  Every translation unit under csrc/ is compiled with
+`-gencode arch=compute_100a,code=sm_100a -lineinfo`; the objects are cached by source hash.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "msmctts", "_b200")
+OBJ_DIR = os.path.join(HERE, "build")
+LIB = os.path.join(OUT_DIR, "libmsmc_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "--use_fast_math=false"] if False else \
+        ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
+def _digest(path, extra):
+    h = hashlib.sha256()
+    h.update(" ".join(FLAGS).encode())
+    for p in [path] + extra:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def build(verbose=True):
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(OUT_DIR, exist_ok=True)
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    headers.append(os.path.join(HERE, "..", "include", "msmc_b200.h"))
+    sources = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    objs, rebuilt = [], False
+    for src in sources:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(OBJ_DIR, "%s.%s.o" % (src[:-3], _digest(path, headers)))
+        if not os.path.exists(obj):
+            cmd = [NVCC] + FLAGS + ["-c", path, "-o", obj]
+            if verbose:
+                print("[build]", " ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+            rebuilt = True
+        objs.append(obj)
+    if rebuilt or not os.path.exists(LIB):
+        cmd = [NVCC, "-shared", "-cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64", "-o", LIB] + objs
+        if verbose:
+            print("[build]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build())

@@ -1,0 +1,711 @@
+// Implicit-GEMM convolution family, fp32 CUDA-core path (first correct path; the tcgen05 TF32 path in
+// conv_umma.cu takes the large stride-1 shapes).  One tile engine, three loaders:
+//   conv_gemm_kernel  : forward form and conv-transpose form (phase-decomposed so no tap is wasted)
+//   conv_wgrad_kernel : weight gradient, split over output rows, partials reduced deterministically
+// Replaces torch.nn.Conv1d / ConvTranspose1d / Conv2d / Linear forward+backward at the call sites
+// listed in include/msmc_b200.h.
+#include "common.cuh"
+#include <algorithm>
+
+namespace msmc {
+namespace {
+
+constexpr int BM = 128;   // rows of the output tile held by one CTA
+constexpr int BK = 16;    // reduction chunk
+constexpr int NTHREADS = 256;
+constexpr int MAX_TAPS_TABLE = 1024;
+
+struct ConvArgs {
+  msmc_conv_geom g;
+  const float* src;
+  const float* src_aux;
+  const float* w;
+  const float* bias;
+  const float* residual;
+  const float* dst_aux;
+  float* dst;
+  int vec_src;      // 8-wide contiguous channel loads allowed
+  int b_kmajor;     // weight tile: lanes run along the reduction index (ws_cs == 1)
+};
+
+struct Taps {
+  // valid taps of the current phase; forward form decodes directly
+  int n;
+  const short* kh;
+  const short* kw;
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  // ReflectionPad semantics: -1 -> 1, n -> n-2 (single bounce is enough for pad < n)
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// Source coordinate for destination (hd, wd) and tap (kh, kw). Returns false when the tap reads padding zeros.
+__device__ __forceinline__ bool src_coord(const msmc_conv_geom& g, int hd, int wd, int kh, int kw, int& hs, int& ws) {
+  if (!g.transposed) {
+    hs = hd * g.sh + kh * g.dh - g.ph;
+    ws = wd * g.sw + kw * g.dw - g.pw;
+    if (g.pad_reflect) {
+      hs = reflect_idx(hs, g.Hs);
+      ws = reflect_idx(ws, g.Ws);
+      return true;
+    }
+    return hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
+  } else {
+    int th = hd + g.ph - kh * g.dh;
+    int tw = wd + g.pw - kw * g.dw;
+    if (th < 0 || tw < 0) return false;
+    if (th % g.sh != 0 || tw % g.sw != 0) return false;
+    hs = th / g.sh;
+    ws = tw / g.sw;
+    return hs < g.Hs && ws < g.Ws;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const ConvArgs a) {
+  constexpr int TN = BN / 16;
+  const msmc_conv_geom& g = a.g;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  __shared__ short tap_kh[MAX_TAPS_TABLE];
+  __shared__ short tap_kw[MAX_TAPS_TABLE];
+  __shared__ int s_ntaps;
+
+  const int tid = threadIdx.x;
+  // ---- phase (conv-transpose form only): destination positions with (hd % sh, wd % sw) == (rh, rw)
+  int rh = 0, rw = 0, step_h = 1, step_w = 1;
+  if (g.transposed) {
+    rh = blockIdx.z / g.sw;
+    rw = blockIdx.z % g.sw;
+    step_h = g.sh;
+    step_w = g.sw;
+  }
+  const int Hp = (g.Hd - rh + step_h - 1) / step_h;
+  const int Wp = (g.Wd - rw + step_w - 1) / step_w;
+  const int64_t M = (int64_t)g.B * Hp * Wp;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  if (m0 >= M) return;
+  const int n0 = blockIdx.y * BN;
+
+  int ntaps = g.KH * g.KW;
+  if (g.transposed) {
+    if (tid == 0) {
+      int c = 0;
+      for (int kh = 0; kh < g.KH; ++kh) {
+        int th = rh + g.ph - kh * g.dh;
+        if (((th % g.sh) + g.sh) % g.sh != 0) continue;
+        for (int kw = 0; kw < g.KW; ++kw) {
+          int tw = rw + g.pw - kw * g.dw;
+          if (((tw % g.sw) + g.sw) % g.sw != 0) continue;
+          tap_kh[c] = (short)kh;
+          tap_kw[c] = (short)kw;
+          ++c;
+        }
+      }
+      s_ntaps = c;
+    }
+    __syncthreads();
+    ntaps = s_ntaps;
+  }
+  const int64_t Ktot = (int64_t)ntaps * g.Cs;
+
+  // ---- per-thread A row (fixed over the K loop)
+  const int a_row = tid >> 1;
+  const int a_kpart = (tid & 1) * 8;
+  const int64_t am = m0 + a_row;
+  const bool a_row_ok = am < M;
+  int ab = 0, ahd = 0, awd = 0;
+  if (a_row_ok) {
+    ab = (int)(am / ((int64_t)Hp * Wp));
+    int rem = (int)(am % ((int64_t)Hp * Wp));
+    ahd = rh + (rem / Wp) * step_h;
+    awd = rw + (rem % Wp) * step_w;
+  }
+  // ---- per-thread B coordinates
+  int b_kk, b_nn;
+  if (a.b_kmajor) { b_kk = tid & 15; b_nn = (tid >> 4) * TN; }
+  else            { b_kk = tid >> 4; b_nn = (tid & 15) * TN; }
+
+  float areg[8];
+  float breg[TN];
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int ty = tid >> 4, tx = tid & 15;
+  const bool need_aux = xf_needs_aux(g.src_xf);
+
+  auto decode_tap = [&](int t, int& kh, int& kw) {
+    if (g.transposed) { kh = tap_kh[t]; kw = tap_kw[t]; }
+    else { kh = t / g.KW; kw = t - kh * g.KW; }
+  };
+
+  auto load_tiles = [&](int64_t k0) {
+    // A: 8 consecutive reduction indices of one output row
+    const int64_t kb = k0 + a_kpart;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) areg[i] = 0.f;
+    if (a_row_ok && kb < Ktot) {
+      if (a.vec_src) {
+        int t = (int)(kb / g.Cs);
+        int c = (int)(kb - (int64_t)t * g.Cs);
+        int kh, kw, hs, ws;
+        decode_tap(t, kh, kw);
+        if (src_coord(g, ahd, awd, kh, kw, hs, ws)) {
+          const int64_t off = (((int64_t)ab * g.Hs + hs) * g.Ws + ws);
+          const float4* p = reinterpret_cast<const float4*>(a.src + off * g.ld_src + c);
+          float4 v0 = __ldg(p), v1 = __ldg(p + 1);
+          areg[0] = v0.x; areg[1] = v0.y; areg[2] = v0.z; areg[3] = v0.w;
+          areg[4] = v1.x; areg[5] = v1.y; areg[6] = v1.z; areg[7] = v1.w;
+          if (g.src_xf != MSMC_XF_NONE) {
+            float aux[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (need_aux) {
+              const float4* q = reinterpret_cast<const float4*>(a.src_aux + off * g.ld_saux + c);
+              float4 u0 = __ldg(q), u1 = __ldg(q + 1);
+              aux[0] = u0.x; aux[1] = u0.y; aux[2] = u0.z; aux[3] = u0.w;
+              aux[4] = u1.x; aux[5] = u1.y; aux[6] = u1.z; aux[7] = u1.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) areg[i] = apply_xf(g.src_xf, g.src_slope, areg[i], aux[i]);
+          }
+        }
+      } else {
+        int t = (int)(kb / g.Cs);
+        int c = (int)(kb - (int64_t)t * g.Cs);
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          if (kb + i < Ktot) {
+            int kh, kw, hs, ws;
+            decode_tap(t, kh, kw);
+            if (src_coord(g, ahd, awd, kh, kw, hs, ws)) {
+              const int64_t off = (((int64_t)ab * g.Hs + hs) * g.Ws + ws);
+              float v = __ldg(a.src + off * g.ld_src + c);
+              float aux = need_aux ? __ldg(a.src_aux + off * g.ld_saux + c) : 0.f;
+              areg[i] = apply_xf(g.src_xf, g.src_slope, v, aux);
+            }
+          }
+          if (++c == g.Cs) { c = 0; ++t; }
+        }
+      }
+    }
+    // B: weights
+    const int64_t k = k0 + b_kk;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) breg[j] = 0.f;
+    if (k < Ktot) {
+      int t = (int)(k / g.Cs);
+      int c = (int)(k - (int64_t)t * g.Cs);
+      int kh, kw;
+      decode_tap(t, kh, kw);
+      const float* wp = a.w + kh * g.ws_kh + kw * g.ws_kw + c * g.ws_cs;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        int n = n0 + b_nn + j;
+        if (n < g.Cd) breg[j] = __ldg(wp + (int64_t)n * g.ws_cd);
+      }
+    }
+  };
+
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) As[a_kpart + i][a_row] = areg[i];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) Bs[b_kk][b_nn + j] = breg[j];
+  };
+
+  load_tiles(0);
+  store_tiles();
+  __syncthreads();
+  for (int64_t k0 = 0; k0 < Ktot; k0 += BK) {
+    const bool has_next = (k0 + BK) < Ktot;
+    if (has_next) load_tiles(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[8], bv[TN];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+      av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (has_next) {
+      store_tiles();
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue: bias, result transform, residual
+  const bool dneed_aux = xf_needs_aux(g.dst_xf);
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + ty * 8 + i;
+    if (m >= M) break;
+    const int b = (int)(m / ((int64_t)Hp * Wp));
+    const int rem = (int)(m % ((int64_t)Hp * Wp));
+    const int hd = rh + (rem / Wp) * step_h;
+    const int wd = rw + (rem % Wp) * step_w;
+    const int64_t row = ((int64_t)b * g.Hd + hd) * g.Wd + wd;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n < g.Cd) {
+        float v = acc[i][j];
+        if (a.bias) v += __ldg(a.bias + n);
+        if (g.dst_xf != MSMC_XF_NONE) {
+          float aux = dneed_aux ? __ldg(a.dst_aux + row * g.ld_daux + n) : 0.f;
+          v = apply_xf(g.dst_xf, g.dst_slope, v, aux);
+        }
+        if (a.residual) v += __ldg(a.residual + row * g.ld_res + n);
+        a.dst[row * g.ld_dst + n] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient:  dW[(tap,cs), cd] = sum_m  xf(src)[m,(tap,cs)] * xf(gout)[m, cd]
+// ------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  msmc_conv_geom g;
+  const float* src;
+  const float* src_aux;
+  const float* gout;
+  const float* gout_aux;
+  float* partial;         // [splits][Ktot*Cd + Cd]
+  int64_t rows_per_split; // multiple of BK
+  int vec_src;
+  int want_bias;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const WgradArgs a) {
+  constexpr int TN = BN / 16;
+  const msmc_conv_geom& g = a.g;
+  __shared__ __align__(16) float As[BK][BM + 4];   // [row m within chunk][reduction-index tile]
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  __shared__ float bias_red[BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
+  const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
+  const int64_t kt0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int64_t mbeg = (int64_t)blockIdx.z * a.rows_per_split;
+  const int64_t mend = min(M, mbeg + a.rows_per_split);
+
+  const int l_mm = tid >> 4;              // row within the chunk (0..15)
+  const int l_kpart = (tid & 15) * 8;     // 8 consecutive reduction indices
+  const int l_nn = (tid & 15) * TN;
+  const int ty = tid >> 4, tx = tid & 15;
+  const bool need_aux = xf_needs_aux(g.src_xf);
+  const bool gneed_aux = xf_needs_aux(g.dst_xf);
+  const bool do_bias = a.want_bias && blockIdx.x == 0;
+
+  float areg[8], breg[TN], bsum[TN];
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < TN; ++j) bsum[j] = 0.f;
+
+  // the (tap, channel) of this thread's 8 reduction indices never changes over the row loop
+  const int64_t kb = kt0 + l_kpart;
+
+  auto load_tiles = [&](int64_t mb) {
+    const int64_t m = mb + l_mm;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) areg[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) breg[j] = 0.f;
+    if (m < mend) {
+      const int b = (int)(m / ((int64_t)g.Hd * g.Wd));
+      const int rem = (int)(m % ((int64_t)g.Hd * g.Wd));
+      const int hd = rem / g.Wd, wd = rem % g.Wd;
+      if (kb < Ktot) {
+        int t = (int)(kb / g.Cs);
+        int c = (int)(kb - (int64_t)t * g.Cs);
+        if (a.vec_src) {
+          int kh = t / g.KW, kw = t - kh * g.KW, hs, ws;
+          if (src_coord(g, hd, wd, kh, kw, hs, ws)) {
+            const int64_t off = (((int64_t)b * g.Hs + hs) * g.Ws + ws);
+            const float4* p = reinterpret_cast<const float4*>(a.src + off * g.ld_src + c);
+            float4 v0 = __ldg(p), v1 = __ldg(p + 1);
+            areg[0] = v0.x; areg[1] = v0.y; areg[2] = v0.z; areg[3] = v0.w;
+            areg[4] = v1.x; areg[5] = v1.y; areg[6] = v1.z; areg[7] = v1.w;
+            if (g.src_xf != MSMC_XF_NONE) {
+              float aux[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              if (need_aux) {
+                const float4* q = reinterpret_cast<const float4*>(a.src_aux + off * g.ld_saux + c);
+                float4 u0 = __ldg(q), u1 = __ldg(q + 1);
+                aux[0] = u0.x; aux[1] = u0.y; aux[2] = u0.z; aux[3] = u0.w;
+                aux[4] = u1.x; aux[5] = u1.y; aux[6] = u1.z; aux[7] = u1.w;
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) areg[i] = apply_xf(g.src_xf, g.src_slope, areg[i], aux[i]);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            if (kb + i < Ktot) {
+              int kh = t / g.KW, kw = t - kh * g.KW, hs, ws;
+              if (src_coord(g, hd, wd, kh, kw, hs, ws)) {
+                const int64_t off = (((int64_t)b * g.Hs + hs) * g.Ws + ws);
+                float v = __ldg(a.src + off * g.ld_src + c);
+                float aux = need_aux ? __ldg(a.src_aux + off * g.ld_saux + c) : 0.f;
+                areg[i] = apply_xf(g.src_xf, g.src_slope, v, aux);
+              }
+            }
+            if (++c == g.Cs) { c = 0; ++t; }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int n = n0 + l_nn + j;
+        if (n < g.Cd) {
+          float v = __ldg(a.gout + m * g.ld_dst + n);
+          if (g.dst_xf != MSMC_XF_NONE) {
+            float aux = gneed_aux ? __ldg(a.gout_aux + m * g.ld_daux + n) : 0.f;
+            v = apply_xf(g.dst_xf, g.dst_slope, v, aux);
+          }
+          breg[j] = v;
+        }
+      }
+    }
+  };
+  auto store_tiles = [&]() {
+    *reinterpret_cast<float4*>(&As[l_mm][l_kpart]) = make_float4(areg[0], areg[1], areg[2], areg[3]);
+    *reinterpret_cast<float4*>(&As[l_mm][l_kpart + 4]) = make_float4(areg[4], areg[5], areg[6], areg[7]);
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      Bs[l_mm][l_nn + j] = breg[j];
+      bsum[j] += breg[j];
+    }
+  };
+
+  if (mbeg < mend) {
+    load_tiles(mbeg);
+    store_tiles();
+  }
+  __syncthreads();
+  for (int64_t mb = mbeg; mb < mend; mb += BK) {
+    const bool has_next = (mb + BK) < mend;
+    if (has_next) load_tiles(mb + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[8], bv[TN];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
+      av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (has_next) {
+      store_tiles();
+      __syncthreads();
+    }
+  }
+
+  float* part = a.partial + (int64_t)blockIdx.z * (Ktot * g.Cd + g.Cd);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t k = kt0 + ty * 8 + i;
+    if (k < Ktot) {
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int n = n0 + tx * TN + j;
+        if (n < g.Cd) part[k * g.Cd + n] = acc[i][j];
+      }
+    }
+  }
+  if (do_bias) {
+    // fixed-order reduction over the 16 row-lanes
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bias_red[l_mm][l_nn + j] = bsum[j];
+    __syncthreads();
+    if (tid < BN) {
+      float s = 0.f;
+      for (int r = 0; r < BK; ++r) s += bias_red[r][tid];
+      const int n = n0 + tid;
+      if (n < g.Cd) part[Ktot * g.Cd + n] = s;
+    }
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const msmc_conv_geom g, const float* __restrict__ partial, int splits,
+                                    float* __restrict__ dw, float* __restrict__ dbias) {
+  const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
+  const int64_t per = Ktot * g.Cd + g.Cd;
+  const int64_t total = dbias ? per : Ktot * g.Cd;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * per + e];
+    if (e < Ktot * g.Cd) {
+      const int64_t k = e / g.Cd;
+      const int n = (int)(e - k * g.Cd);
+      const int t = (int)(k / g.Cs);
+      const int c = (int)(k - (int64_t)t * g.Cs);
+      const int kh = t / g.KW, kw = t - kh * g.KW;
+      dw[kh * g.ws_kh + kw * g.ws_kw + c * g.ws_cs + (int64_t)n * g.ws_cd] = s;
+    } else {
+      dbias[e - Ktot * g.Cd] = s;
+    }
+  }
+}
+
+// weight_norm forward: w = g * v / ||v||_row, written through arbitrary output strides (GEMM layout)
+__global__ void weight_norm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ gpar,
+                                       float* __restrict__ w, float* __restrict__ inv_norm,
+                                       int O, int I, int J, int64_t so, int64_t si, int64_t sj) {
+  const int o = blockIdx.x;
+  const int n = I * J;
+  const float* vr = v + (int64_t)o * n;
+  __shared__ float red[32];
+  __shared__ float s_scale;
+  float scale = 1.f;
+  if (gpar) {
+    float ss = 0.f;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) { float x = vr[e]; ss = fmaf(x, x, ss); }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+      float inv = 1.f / sqrtf(t);
+      if (inv_norm) inv_norm[o] = inv;
+      s_scale = gpar[o] * inv;
+    }
+    __syncthreads();
+    scale = s_scale;
+  }
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int i = e / J, j = e - i * J;
+    w[o * so + i * si + j * sj] = vr[e] * scale;
+  }
+}
+
+// weight_norm backward: dg = (dw . v) / ||v|| ;  dv = g/||v|| * (dw - v * (dw . v)/||v||^2)
+__global__ void weight_norm_bwd_kernel(const float* __restrict__ dw, int64_t so, int64_t si, int64_t sj,
+                                       const float* __restrict__ v, const float* __restrict__ gpar,
+                                       const float* __restrict__ inv_norm, float* __restrict__ dv,
+                                       float* __restrict__ dg, int O, int I, int J) {
+  const int o = blockIdx.x;
+  const int n = I * J;
+  const float* vr = v + (int64_t)o * n;
+  float* dvr = dv + (int64_t)o * n;
+  if (!gpar) {
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const int i = e / J, j = e - i * J;
+      dvr[e] = dw[o * so + i * si + j * sj];
+    }
+    return;
+  }
+  __shared__ float red[32];
+  __shared__ float s_dot;
+  float dot = 0.f;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int i = e / J, j = e - i * J;
+    dot = fmaf(dw[o * so + i * si + j * sj], vr[e], dot);
+  }
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    s_dot = t;
+    dg[o] = t * inv_norm[o];
+  }
+  __syncthreads();
+  const float inv = inv_norm[o];
+  const float gs = gpar[o] * inv;
+  const float coef = s_dot * inv * inv;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int i = e / J, j = e - i * J;
+    dvr[e] = gs * (dw[o * so + i * si + j * sj] - vr[e] * coef);
+  }
+}
+
+// backward of ReflectionPad: fold a (B, H+2p, W+2q, C) gradient onto (B, H, W, C)
+__global__ void reflect_fold_kernel(const float* __restrict__ gp, float* __restrict__ gx, int B, int H, int W,
+                                    int C, int ph, int pw) {
+  const int64_t total = (int64_t)B * H * W * C;
+  const int Hp = H + 2 * ph, Wp = W + 2 * pw;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    int64_t r = e / C;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int b = (int)(r / H);
+    // padded coordinates that reflect onto (h, w): itself, and mirror images near each border
+    int hc[3], wc[3], nh = 0, nw = 0;
+    hc[nh++] = h + ph;
+    if (h >= 1 && h <= ph) hc[nh++] = ph - h;
+    if (h <= H - 2 && h >= H - 1 - ph) hc[nh++] = ph + 2 * (H - 1) - h;
+    wc[nw++] = w + pw;
+    if (w >= 1 && w <= pw) wc[nw++] = pw - w;
+    if (w <= W - 2 && w >= W - 1 - pw) wc[nw++] = pw + 2 * (W - 1) - w;
+    float s = 0.f;
+    for (int i = 0; i < nh; ++i)
+      for (int j = 0; j < nw; ++j) s += gp[(((int64_t)b * Hp + hc[i]) * Wp + wc[j]) * C + c];
+    gx[e] = s;
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int pick_bn(int cd) { return cd <= 16 ? 16 : (cd <= 32 ? 32 : (cd <= 64 ? 64 : 128)); }
+
+}  // namespace
+}  // namespace msmc
+
+using namespace msmc;
+
+extern "C" int msmc_conv_forward(const msmc_conv_geom* gp, const float* src, const float* src_aux,
+                                 const float* w, const float* bias, const float* residual,
+                                 const float* dst_aux, float* dst, void* stream) {
+  MSMC_REQUIRE(gp && src && w && dst);
+  const msmc_conv_geom& g = *gp;
+  MSMC_REQUIRE(g.B > 0 && g.Cs > 0 && g.Cd > 0 && g.KH > 0 && g.KW > 0 && g.sh > 0 && g.sw > 0);
+  MSMC_REQUIRE(g.Hs > 0 && g.Ws > 0 && g.Hd > 0 && g.Wd > 0);
+  MSMC_REQUIRE(!(g.transposed && g.pad_reflect));
+  MSMC_REQUIRE(!xf_needs_aux(g.src_xf) || src_aux);
+  MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || dst_aux);
+  if (g.transposed) MSMC_REQUIRE((int64_t)g.KH * g.KW <= MAX_TAPS_TABLE);
+  if (g.pad_reflect) MSMC_REQUIRE((g.ph == 0 || g.ph < g.Hs) && (g.pw == 0 || g.pw < g.Ws));
+  ConvArgs a;
+  a.g = g; a.src = src; a.src_aux = src_aux; a.w = w; a.bias = bias; a.residual = residual;
+  a.dst_aux = dst_aux; a.dst = dst;
+  a.vec_src = (g.Cs % 8 == 0) && (g.ld_src % 4 == 0) && aligned16(src) &&
+              (!xf_needs_aux(g.src_xf) || ((g.ld_saux % 4 == 0) && aligned16(src_aux)));
+  a.b_kmajor = (g.ws_cd != 1 && g.ws_cs == 1);
+  const int phases = g.transposed ? g.sh * g.sw : 1;
+  int64_t maxM;
+  if (g.transposed) maxM = (int64_t)g.B * ceil_div(g.Hd, g.sh) * ceil_div(g.Wd, g.sw);
+  else maxM = (int64_t)g.B * g.Hd * g.Wd;
+  const int bn = pick_bn(g.Cd);
+  dim3 grid((unsigned)ceil_div64(maxM, BM), (unsigned)ceil_div(g.Cd, bn), (unsigned)phases);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (bn) {
+    case 16: conv_gemm_kernel<16><<<grid, NTHREADS, 0, st>>>(a); break;
+    case 32: conv_gemm_kernel<32><<<grid, NTHREADS, 0, st>>>(a); break;
+    case 64: conv_gemm_kernel<64><<<grid, NTHREADS, 0, st>>>(a); break;
+    default: conv_gemm_kernel<128><<<grid, NTHREADS, 0, st>>>(a); break;
+  }
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+
+namespace {
+int wgrad_splits(const msmc_conv_geom& g) {
+  const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
+  const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
+  const int bn = msmc::pick_bn(g.Cd);
+  const int64_t tiles = ceil_div64(Ktot, BM) * ceil_div(g.Cd, bn);
+  const int64_t target = (int64_t)msmc::num_sms() * 3;
+  int64_t s = ceil_div64(target, tiles);
+  const int64_t max_by_rows = ceil_div64(M, 4 * BK);
+  if (s > max_by_rows) s = max_by_rows;
+  // bound the partial-sum workspace to 96 MiB
+  const int64_t per = (Ktot * g.Cd + g.Cd) * (int64_t)sizeof(float);
+  const int64_t cap = ((int64_t)96 << 20) / per;
+  if (s > cap) s = cap;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+}  // namespace
+
+extern "C" int64_t msmc_conv_wgrad_workspace(const msmc_conv_geom* gp) {
+  if (!gp) return -1;
+  const msmc_conv_geom& g = *gp;
+  const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
+  return (int64_t)wgrad_splits(g) * (Ktot * g.Cd + g.Cd) * (int64_t)sizeof(float);
+}
+
+extern "C" int msmc_conv_wgrad(const msmc_conv_geom* gp, const float* src, const float* src_aux,
+                               const float* gout, const float* gout_aux, float* dw, float* dbias,
+                               float* workspace, int64_t workspace_bytes, void* stream) {
+  MSMC_REQUIRE(gp && src && gout && dw && workspace);
+  const msmc_conv_geom& g = *gp;
+  MSMC_REQUIRE(!g.transposed);
+  MSMC_REQUIRE(!xf_needs_aux(g.src_xf) || src_aux);
+  MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || gout_aux);
+  const int splits = wgrad_splits(g);
+  const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
+  MSMC_REQUIRE(workspace_bytes >= (int64_t)splits * (Ktot * g.Cd + g.Cd) * (int64_t)sizeof(float));
+  const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
+  WgradArgs a;
+  a.g = g; a.src = src; a.src_aux = src_aux; a.gout = gout; a.gout_aux = gout_aux;
+  a.partial = workspace;
+  a.rows_per_split = ceil_div64(ceil_div64(M, splits), BK) * BK;
+  a.vec_src = (g.Cs % 8 == 0) && (g.ld_src % 4 == 0) && aligned16(src) &&
+              (!xf_needs_aux(g.src_xf) || ((g.ld_saux % 4 == 0) && aligned16(src_aux)));
+  a.want_bias = dbias != nullptr;
+  const int bn = pick_bn(g.Cd);
+  dim3 grid((unsigned)ceil_div64(Ktot, BM), (unsigned)ceil_div(g.Cd, bn), (unsigned)splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (bn) {
+    case 16: conv_wgrad_kernel<16><<<grid, NTHREADS, 0, st>>>(a); break;
+    case 32: conv_wgrad_kernel<32><<<grid, NTHREADS, 0, st>>>(a); break;
+    case 64: conv_wgrad_kernel<64><<<grid, NTHREADS, 0, st>>>(a); break;
+    default: conv_wgrad_kernel<128><<<grid, NTHREADS, 0, st>>>(a); break;
+  }
+  MSMC_CHECK_LAUNCH();
+  const int64_t total = Ktot * g.Cd + g.Cd;
+  int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 8);
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(g, workspace, splits, dw, dbias);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+
+extern "C" int msmc_weight_norm_fwd(const float* v, const float* g, float* w, float* inv_norm, int32_t O,
+                                    int32_t I, int32_t J, int64_t so, int64_t si, int64_t sj, void* stream) {
+  MSMC_REQUIRE(v && w && O > 0 && I > 0 && J > 0);
+  weight_norm_fwd_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(v, g, w, inv_norm, O, I, J, so, si, sj);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+
+extern "C" int msmc_weight_norm_bwd(const float* dw, int64_t so, int64_t si, int64_t sj, const float* v,
+                                    const float* g, const float* inv_norm, float* dv, float* dg, int32_t O,
+                                    int32_t I, int32_t J, void* stream) {
+  MSMC_REQUIRE(dw && v && dv && O > 0 && I > 0 && J > 0);
+  MSMC_REQUIRE(!g || (inv_norm && dg));
+  weight_norm_bwd_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(dw, so, si, sj, v, g, inv_norm, dv, dg, O, I, J);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+
+extern "C" int msmc_reflect_pad_fold(const float* gpad, float* gx, int32_t B, int32_t H, int32_t W, int32_t C,
+                                     int32_t ph, int32_t pw, void* stream) {
+  MSMC_REQUIRE(gpad && gx && B > 0 && H > 0 && W > 0 && C > 0 && ph >= 0 && pw >= 0);
+  MSMC_REQUIRE((ph < H || ph == 0) && (pw < W || pw == 0));
+  const int64_t total = (int64_t)B * H * W * C;
+  int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 16);
+  reflect_fold_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gpad, gx, B, H, W, C, ph, pw);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}

@@ -1,0 +1,375 @@
+// Multi-head VQ: nearest-codeword search, EMA codebook update, straight-through backward, triplet loss.
+// Replaces Quantize.forward / MultiHeadQuantize.forward / Quantize.compute_triple_loss
+// (reference vqgantts/modules.py:24-67, 86-116, 137-169).
+//
+// Search kernel: the head's codebook (dim x K, dim-major, exactly the reference's `embed` buffer) is staged in
+// shared memory once per CTA together with ||e_k||^2; one warp owns one row at a time, lane l scores codewords
+// l, l+32, ... with the row broadcast by warp shuffle, and the argmin is a warp-shuffle reduction (lowest index
+// wins ties).  Distances use the reference's expanded form (||z||^2 - 2 z.e_k) + ||e_k||^2 in true fp32 with a
+// fixed, sequential fma order that the C oracle (oracle/vq_oracle.c) reproduces bit for bit.
+// HBM-bound integer/float gather work: no tensor cores.
+#include "common.cuh"
+#include <algorithm>
+
+namespace msmc {
+namespace {
+
+constexpr int VQ_WARPS = 8;
+constexpr int MAX_KPL = 16;  // codewords per lane -> n_embed <= 512
+
+template <int DIM, int KPL>
+__global__ void __launch_bounds__(VQ_WARPS * 32)
+vq_search_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restrict__ embed,
+                 float* __restrict__ quant_raw, float* __restrict__ quant_st, float* __restrict__ diff,
+                 int64_t* __restrict__ idx, int n_rows, int n_heads, int K, int rows_per_cta) {
+  extern __shared__ float smem[];
+  float* cb = smem;                  // [DIM][K]
+  float* ee = smem + (size_t)DIM * K;  // [K]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_beg = blockIdx.x * rows_per_cta;
+  const int row_end = min(n_rows, row_beg + rows_per_cta);
+  const float inv_heads = 1.f / (float)n_heads;
+  constexpr int DPL = DIM / 32;  // dims per lane
+
+  for (int h = 0; h < n_heads; ++h) {
+    __syncthreads();  // previous head's codebook fully consumed
+    const float* e_h = embed + (size_t)h * DIM * K;
+    for (int i = threadIdx.x; i < DIM * K; i += blockDim.x) cb[i] = e_h[i];
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float s = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < DIM; ++d) { float v = cb[d * K + k]; s = fmaf(v, v, s); }
+      ee[k] = s;
+    }
+    __syncthreads();
+
+    for (int r = row_beg + warp; r < row_end; r += VQ_WARPS) {
+      const float* zr = z + (int64_t)r * ld_z + h * DIM;
+      float zl[DPL];
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) zl[j] = zr[lane + 32 * j];
+      float dot[KPL];
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) dot[j] = 0.f;
+      float zz = 0.f;
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) {
+#pragma unroll 8
+        for (int dl = 0; dl < 32; ++dl) {
+          // sequential over d = 32*j + dl: every lane sees the same broadcast value
+          const float zd = __shfl_sync(0xffffffffu, zl[j], dl);
+          zz = fmaf(zd, zd, zz);
+          const float* cr = cb + (size_t)(32 * j + dl) * K + lane;
+#pragma unroll
+          for (int q = 0; q < KPL; ++q) {
+            const int k = lane + 32 * q;
+            if (k < K) dot[q] = fmaf(zd, cr[32 * q], dot[q]);
+          }
+        }
+      }
+      float best = INFINITY;
+      int best_k = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < KPL; ++q) {
+        const int k = lane + 32 * q;
+        if (k < K) {
+          const float dist = (zz - 2.f * dot[q]) + ee[k];
+          if (dist < best || (dist == best && k < best_k)) { best = dist; best_k = k; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+        if (ob < best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
+      }
+      if (lane == 0) idx[(int64_t)r * n_heads + h] = (int64_t)best_k;
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) {
+        const int d = lane + 32 * j;
+        const float q = cb[d * K + best_k];
+        const float x = zl[j];
+        const int64_t o = (int64_t)r * (n_heads * DIM) + h * DIM + d;
+        quant_raw[o] = q;
+        quant_st[o] = x + (q - x);
+        const float dq = q - x;
+        const float dv = __fmul_rn(dq, dq);   // no fma contraction with the head sum below (matches the C oracle)
+        float* dp = diff + (int64_t)r * DIM + d;
+        // sum over heads in head order (python `sum(diffs)`), then / n_heads
+        float acc = (h == 0) ? dv : __fadd_rn(*dp, dv);
+        if (h == n_heads - 1) acc *= inv_heads;
+        *dp = acc;
+      }
+    }
+  }
+}
+
+// One CTA per (head, codeword): masked count and masked sum of the rows assigned to it, then the EMA.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+vq_ema_accum_kernel(const float* __restrict__ z, int64_t ld_z, const int64_t* __restrict__ idx,
+                    const int* __restrict__ lengths, int batch, int t, int n_heads, int K, float decay,
+                    float* __restrict__ cluster_size, float* __restrict__ embed_avg) {
+  const int h = blockIdx.x / K, k = blockIdx.x % K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  constexpr int DPL = DIM / 32;
+  __shared__ float s_sum[8][DIM];
+  __shared__ float s_cnt[8];
+  float acc[DPL];
+#pragma unroll
+  for (int j = 0; j < DPL; ++j) acc[j] = 0.f;
+  float cnt = 0.f;
+  const int n_rows = batch * t;
+  // each warp scans a contiguous slab so the summation order is fixed by (warp, row)
+  const int slab = ((n_rows + nwarps - 1) / nwarps + 31) / 32 * 32;
+  const int rbeg = warp * slab, rend = min(n_rows, rbeg + slab);
+  for (int r0 = rbeg; r0 < rend; r0 += 32) {
+    const int r = r0 + lane;
+    bool hit = false;
+    if (r < rend) {
+      const int b = r / t, i = r - b * t;
+      hit = (i < lengths[b]) && (idx[(int64_t)r * n_heads + h] == (int64_t)k);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    while (m) {
+      const int s = __ffs(m) - 1;
+      m &= m - 1;
+      const float* zr = z + (int64_t)(r0 + s) * ld_z + h * DIM;
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) acc[j] += zr[lane + 32 * j];
+      cnt += 1.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DPL; ++j) s_sum[warp][lane + 32 * j] = acc[j];
+  if (lane == 0) s_cnt[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x < DIM) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += s_sum[w][threadIdx.x];
+    float* ea = embed_avg + ((size_t)h * DIM + threadIdx.x) * K + k;
+    *ea = *ea * decay + s * (1.f - decay);   // mul_(decay).add_(sum, alpha=1-decay)
+  }
+  if (threadIdx.x == 0) {
+    float c = 0.f;
+    for (int w = 0; w < nwarps; ++w) c += s_cnt[w];
+    float* cs = cluster_size + (size_t)h * K + k;
+    *cs = *cs * decay + c * (1.f - decay);
+  }
+}
+
+// One CTA per head: Laplace-smoothed renormalisation and codebook overwrite (modules.py:49-57)
+template <int DIM>
+__global__ void __launch_bounds__(256)
+vq_ema_finalize_kernel(const float* __restrict__ cluster_size, const float* __restrict__ embed_avg,
+                       float* __restrict__ embed, int K, float eps) {
+  const int h = blockIdx.x;
+  __shared__ float s_n;
+  if (threadIdx.x < 32) {
+    // fixed-order sum: lane-strided partials, then a shuffle tree
+    float s = 0.f;
+    for (int k = threadIdx.x; k < K; k += 32) s += cluster_size[(size_t)h * K + k];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) s_n = s;
+  }
+  __syncthreads();
+  const float n = s_n;
+  for (int e = threadIdx.x; e < DIM * K; e += blockDim.x) {
+    const int k = e % K;
+    const float cs = (cluster_size[(size_t)h * K + k] + eps) / (n + K * eps) * n;
+    embed[(size_t)h * DIM * K + e] = embed_avg[(size_t)h * DIM * K + e] / cs;
+  }
+}
+
+__global__ void vq_backward_kernel(const float* __restrict__ g_quant, const float* __restrict__ g_diff,
+                                   const float* __restrict__ z, const float* __restrict__ q,
+                                   float* __restrict__ gz, int64_t total, int n_heads, int dim) {
+  const float c = 2.f / (float)n_heads;
+  const int width = n_heads * dim;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / width;
+    const int d = (int)(e % width) % dim;
+    float g = g_quant ? g_quant[e] : 0.f;
+    if (g_diff) g += c * g_diff[r * dim + d] * (z[e] - q[e]);
+    gz[e] = g;
+  }
+}
+
+// triplet loss per (row, head); one warp per (row, head).  loss(row) = mean_h  red_k  mask * clamp(pos - dist_k + margin, 0) / dim
+template <int DIM>
+__global__ void __launch_bounds__(256)
+vq_triple_kernel(const float* __restrict__ pred, int64_t ld_pred, const float* __restrict__ embed,
+                 const int64_t* __restrict__ target, float* __restrict__ loss_rh, float* __restrict__ gpred,
+                 int n_rows, int n_heads, int K, float margin, int reduce_mean) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= n_rows * n_heads) return;
+  const int r = gw / n_heads, h = gw % n_heads;
+  constexpr int DPL = DIM / 32;
+  const float* pr = pred + (int64_t)r * ld_pred + h * DIM;
+  const float* e_h = embed + (size_t)h * DIM * K;
+  const int tk = (int)target[(int64_t)r * n_heads + h];
+  float pl[DPL], tl[DPL];
+  float zz = 0.f, pos = 0.f;
+#pragma unroll
+  for (int j = 0; j < DPL; ++j) {
+    pl[j] = pr[lane + 32 * j];
+    tl[j] = e_h[(size_t)(lane + 32 * j) * K + tk];
+    zz = fmaf(pl[j], pl[j], zz);
+    const float dd = pl[j] - tl[j];
+    pos = fmaf(dd, dd, pos);
+  }
+  zz = warp_sum(zz);
+  pos = warp_sum(pos);
+  const float scale = (reduce_mean ? 1.f / (float)K : 1.f) / (float)DIM / (float)n_heads;
+  float lsum = 0.f;
+  float gacc[DPL];
+#pragma unroll
+  for (int j = 0; j < DPL; ++j) gacc[j] = 0.f;
+  float nactive = 0.f;  // number of active hinge terms (for d pos / d pred)
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int k = k0 + lane;
+    float dot = 0.f, eek = 0.f;
+    for (int d = 0; d < DIM; ++d) {
+      const float pd = __shfl_sync(0xffffffffu, pl[d >> 5], d & 31);
+      if (k < K) {
+        const float ev = e_h[(size_t)d * K + k];
+        dot = fmaf(pd, ev, dot);
+        eek = fmaf(ev, ev, eek);
+      }
+    }
+    bool active = false;
+    if (k < K) {
+      const float dist = (zz - 2.f * dot) + eek;
+      const float tl_ = pos - dist;
+      if (tl_ != 0.f) {
+        const float v = tl_ + margin;
+        if (v > 0.f) { lsum += v; active = true; }
+      }
+    }
+    if (gpred) {
+      // d(-dist_k)/d pred = -2 (pred - e_k)
+      unsigned m = __ballot_sync(0xffffffffu, active);
+      nactive += (float)__popc(m);
+      while (m) {
+        const int s = __ffs(m) - 1;
+        m &= m - 1;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j)
+          gacc[j] -= 2.f * (pl[j] - e_h[(size_t)(lane + 32 * j) * K + (k0 + s)]);
+      }
+    }
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) loss_rh[gw] = lsum * scale;
+  if (gpred) {
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
+      const float g = gacc[j] + nactive * 2.f * (pl[j] - tl[j]);
+      gpred[(int64_t)r * (n_heads * DIM) + h * DIM + lane + 32 * j] = g * scale;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace msmc
+
+using namespace msmc;
+
+extern "C" int msmc_vq_search(const float* z, int64_t ld_z, const float* embed, float* quant_raw,
+                              float* quant_st, float* diff, int64_t* idx, int32_t n_rows, int32_t n_heads,
+                              int32_t dim, int32_t n_embed, void* stream) {
+  MSMC_REQUIRE(z && embed && quant_raw && quant_st && diff && idx);
+  MSMC_REQUIRE(n_rows > 0 && n_heads > 0 && n_embed > 0 && n_embed <= 32 * MAX_KPL);
+  if (dim != 64 && dim != 32 && dim != 128 && dim != 256) return MSMC_ERR_UNSUPPORTED;
+  const size_t smem = ((size_t)dim * n_embed + n_embed) * sizeof(float);
+  if (smem > 200 * 1024) return MSMC_ERR_UNSUPPORTED;
+  // fill the machine: at least 8 rows (one per warp) per CTA, at most ~2 CTAs per SM in flight
+  int rows_per_cta = std::max(VQ_WARPS, (int)ceil_div(n_rows, 2 * num_sms()));
+  rows_per_cta = ceil_div(rows_per_cta, VQ_WARPS) * VQ_WARPS;
+  const int grid = ceil_div(n_rows, rows_per_cta);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kpl = ceil_div(n_embed, 32);
+#define LAUNCH_VQ2(D, Q)                                                                                    \
+  do {                                                                                                      \
+    if (smem > 48 * 1024)                                                                                   \
+      cudaFuncSetAttribute(vq_search_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    vq_search_kernel<D, Q><<<grid, VQ_WARPS * 32, smem, st>>>(z, ld_z, embed, quant_raw, quant_st, diff,   \
+                                                               idx, n_rows, n_heads, n_embed, rows_per_cta);\
+  } while (0)
+#define LAUNCH_VQ(D)                                  \
+  do {                                                \
+    if (kpl <= 1) LAUNCH_VQ2(D, 1);                   \
+    else if (kpl <= 2) LAUNCH_VQ2(D, 2);              \
+    else if (kpl <= 4) LAUNCH_VQ2(D, 4);              \
+    else if (kpl <= 8) LAUNCH_VQ2(D, 8);              \
+    else LAUNCH_VQ2(D, 16);                           \
+  } while (0)
+  switch (dim) {
+    case 32: LAUNCH_VQ(32); break;
+    case 64: LAUNCH_VQ(64); break;
+    case 128: LAUNCH_VQ(128); break;
+    default: LAUNCH_VQ(256); break;
+  }
+#undef LAUNCH_VQ
+#undef LAUNCH_VQ2
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+
+extern "C" int msmc_vq_ema_update(const float* z, int64_t ld_z, const int64_t* idx, const int32_t* lengths,
+                                  int32_t batch, int32_t t, int32_t n_heads, int32_t dim, int32_t n_embed,
+                                  float decay, float eps, float* cluster_size, float* embed_avg, float* embed,
+                                  void* stream) {
+  MSMC_REQUIRE(z && idx && lengths && cluster_size && embed_avg && embed);
+  MSMC_REQUIRE(batch > 0 && t > 0 && n_heads > 0 && n_embed > 0);
+  if (dim != 64 && dim != 32 && dim != 128 && dim != 256) return MSMC_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_EMA(D)                                                                                        \
+  do {                                                                                                       \
+    vq_ema_accum_kernel<D><<<n_heads * n_embed, 256, 0, st>>>(z, ld_z, idx, lengths, batch, t, n_heads,      \
+                                                               n_embed, decay, cluster_size, embed_avg);      \
+    vq_ema_finalize_kernel<D><<<n_heads, 256, 0, st>>>(cluster_size, embed_avg, embed, n_embed, eps);        \
+  } while (0)
+  switch (dim) {
+    case 32: LAUNCH_EMA(32); break;
+    case 64: LAUNCH_EMA(64); break;
+    case 128: LAUNCH_EMA(128); break;
+    default: LAUNCH_EMA(256); break;
+  }
+#undef LAUNCH_EMA
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+
+extern "C" int msmc_vq_backward(const float* g_quant, const float* g_diff, const float* z,
+                                const float* quant_raw, float* gz, int32_t n_rows, int32_t n_heads,
+                                int32_t dim, void* stream) {
+  MSMC_REQUIRE(z && quant_raw && gz && n_rows > 0 && n_heads > 0 && dim > 0);
+  const int64_t total = (int64_t)n_rows * n_heads * dim;
+  const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 16);
+  vq_backward_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g_quant, g_diff, z, quant_raw, gz, total,
+                                                               n_heads, dim);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+
+extern "C" int msmc_vq_triple_loss(const float* pred, int64_t ld_pred, const float* embed,
+                                   const int64_t* target, float* loss, float* gpred, int32_t n_rows,
+                                   int32_t n_heads, int32_t dim, int32_t n_embed, float margin,
+                                   int32_t reduce_mean, void* stream) {
+  MSMC_REQUIRE(pred && embed && target && loss && n_rows > 0 && n_heads > 0 && n_embed > 0);
+  if (dim != 64 && dim != 32 && dim != 128 && dim != 256) return MSMC_ERR_UNSUPPORTED;
+  const int warps = n_rows * n_heads;
+  const int blocks = ceil_div(warps, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dim) {
+    case 32: vq_triple_kernel<32><<<blocks, 256, 0, st>>>(pred, ld_pred, embed, target, loss, gpred, n_rows, n_heads, n_embed, margin, reduce_mean); break;
+    case 64: vq_triple_kernel<64><<<blocks, 256, 0, st>>>(pred, ld_pred, embed, target, loss, gpred, n_rows, n_heads, n_embed, margin, reduce_mean); break;
+    case 128: vq_triple_kernel<128><<<blocks, 256, 0, st>>>(pred, ld_pred, embed, target, loss, gpred, n_rows, n_heads, n_embed, margin, reduce_mean); break;
+    default: vq_triple_kernel<256><<<blocks, 256, 0, st>>>(pred, ld_pred, embed, target, loss, gpred, n_rows, n_heads, n_embed, margin, reduce_mean); break;
+  }
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}

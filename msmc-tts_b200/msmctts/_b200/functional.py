@@ -1,0 +1,564 @@
+"""Autograd glue over the C-ABI kernels (host code stays Python/PyTorch; every op below is a hand-written
+sm_100a kernel in csrc/).  Activations are channels-last: (B, H, W, C) with H == 1 for sequences.
+"""
+import ctypes as C
+from collections import namedtuple
+
+import torch
+
+from . import lib as L
+
+ConvCfg = namedtuple("ConvCfg", "KH KW sh sw dh dw ph pw reflect transposed wstr Cd pre_slope post out_hw")
+# wstr = element strides of the weight tensor for (kh, kw, cs, cd), cs = channels of the op's INPUT
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def _rows(x):
+    """channels-last 4-D tensor with unit channel stride and packed rows; returns (tensor, row_pitch)."""
+    assert x.dim() == 4
+    B, H, W, Cn = x.shape
+    ok = (Cn == 1 or x.stride(3) == 1)
+    ld, expect = None, None
+    for n, s in ((W, x.stride(2)), (H, x.stride(1)), (B, x.stride(0))):
+        if n == 1:
+            continue
+        if ld is None:
+            ld, expect = s, s * n
+        else:
+            ok = ok and s == expect
+            expect = s * n
+    if ld is None:
+        ld = Cn
+    if not ok or ld < Cn:
+        x = x.contiguous()
+        ld = Cn
+    return x, ld
+
+
+def conv_out_size(n, k, s, d, p, transposed):
+    if transposed:
+        return (n - 1) * s - 2 * p + d * (k - 1) + 1
+    return (n + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+def _launch_conv(src, w, wstr, bias, residual, dst, KH, KW, sh, sw, dh, dw, ph, pw, reflect, transposed,
+                 src_xf=(L.XF_NONE, 0.0, None), dst_xf=(L.XF_NONE, 0.0, None)):
+    src, ld_src = _rows(src)
+    B, Hs, Ws, Cs = src.shape
+    _, Hd, Wd, Cd = dst.shape
+    assert dst.is_contiguous()
+    g = L.ConvGeom()
+    g.B, g.Hs, g.Ws, g.Cs, g.Hd, g.Wd, g.Cd = B, Hs, Ws, Cs, Hd, Wd, Cd
+    g.KH, g.KW, g.sh, g.sw, g.dh, g.dw, g.ph, g.pw = KH, KW, sh, sw, dh, dw, ph, pw
+    g.pad_reflect, g.transposed = int(reflect), int(transposed)
+    g.ld_src, g.ld_dst = ld_src, Cd
+    res = None
+    if residual is not None:
+        res, g.ld_res = _rows(residual)
+    saux = daux = None
+    if src_xf[2] is not None:
+        saux, g.ld_saux = _rows(src_xf[2])
+    if dst_xf[2] is not None:
+        daux, g.ld_daux = _rows(dst_xf[2])
+    g.ws_kh, g.ws_kw, g.ws_cs, g.ws_cd = wstr
+    g.src_xf, g.src_slope = src_xf[0], float(src_xf[1])
+    g.dst_xf, g.dst_slope = dst_xf[0], float(dst_xf[1])
+    L.require_cuda(src, w, dst)
+    L.call("msmc_conv_forward", C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(w), L.ptr(bias), L.ptr(res),
+           L.ptr(daux), L.ptr(dst))
+    return dst
+
+
+def _launch_wgrad(src, gout, dw, wstr, dbias, KH, KW, sh, sw, dh, dw_, ph, pw, reflect,
+                  src_xf=(L.XF_NONE, 0.0, None), gout_xf=(L.XF_NONE, 0.0, None)):
+    """dW[kh,kw,cs,cd] = sum_rows xf(src)[gathered] * xf(gout);  rows = positions of gout (forward form)."""
+    src, ld_src = _rows(src)
+    gout, ld_g = _rows(gout)
+    B, Hs, Ws, Cs = src.shape
+    _, Hd, Wd, Cd = gout.shape
+    g = L.ConvGeom()
+    g.B, g.Hs, g.Ws, g.Cs, g.Hd, g.Wd, g.Cd = B, Hs, Ws, Cs, Hd, Wd, Cd
+    g.KH, g.KW, g.sh, g.sw, g.dh, g.dw, g.ph, g.pw = KH, KW, sh, sw, dh, dw_, ph, pw
+    g.pad_reflect, g.transposed = int(reflect), 0
+    g.ld_src, g.ld_dst = ld_src, ld_g
+    saux = daux = None
+    if src_xf[2] is not None:
+        saux, g.ld_saux = _rows(src_xf[2])
+    if gout_xf[2] is not None:
+        daux, g.ld_daux = _rows(gout_xf[2])
+    g.ws_kh, g.ws_kw, g.ws_cs, g.ws_cd = wstr
+    g.src_xf, g.src_slope = src_xf[0], float(src_xf[1])
+    g.dst_xf, g.dst_slope = gout_xf[0], float(gout_xf[1])
+    lib = L.load()
+    nbytes = lib.msmc_conv_wgrad_workspace(C.byref(g))
+    ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=src.device)
+    L.call("msmc_conv_wgrad", C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(gout), L.ptr(daux), L.ptr(dw),
+           L.ptr(dbias), L.ptr(ws), C.c_int64(nbytes))
+
+
+# post = (kind, slope): result transform fused in the conv epilogue, and the operand modifier its backward needs
+_POST_FWD = {"none": L.XF_NONE, "relu": L.XF_RELU, "tanh": L.XF_TANH, "lrelu": L.XF_LRELU}
+_POST_BWD = {"none": L.XF_NONE, "relu": L.XF_MUL_DRELU, "tanh": L.XF_MUL_DTANH, "lrelu": L.XF_MUL_DLRELU}
+
+
+class _ConvFn(torch.autograd.Function):
+    """y = post(conv(pre(x), w) + bias) + residual, forward form or conv-transpose form."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, residual, cfg):
+        x, _ = _rows(x)
+        B, Hs, Ws, Cs = x.shape
+        if cfg.out_hw is not None:
+            Hd, Wd = cfg.out_hw
+        else:
+            Hd = conv_out_size(Hs, cfg.KH, cfg.sh, cfg.dh, cfg.ph, cfg.transposed)
+            Wd = conv_out_size(Ws, cfg.KW, cfg.sw, cfg.dw, cfg.pw, cfg.transposed)
+        y = torch.empty((B, Hd, Wd, cfg.Cd), dtype=torch.float32, device=x.device)
+        pre = (L.XF_LRELU, cfg.pre_slope, None) if cfg.pre_slope is not None else (L.XF_NONE, 0.0, None)
+        kind, pslope = cfg.post
+        assert not (kind != "none" and residual is not None)
+        _launch_conv(x, w, cfg.wstr, bias, residual, y, cfg.KH, cfg.KW, cfg.sh, cfg.sw, cfg.dh, cfg.dw, cfg.ph,
+                     cfg.pw, cfg.reflect, cfg.transposed, src_xf=pre, dst_xf=(_POST_FWD[kind], pslope, None))
+        ctx.cfg = cfg
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, w, y if kind != "none" else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        cfg = ctx.cfg
+        x, w, y = ctx.saved_tensors
+        gy = gy.contiguous()
+        kind, pslope = cfg.post
+        # (the sign of a leaky-relu output equals the sign of its input, so y serves as the aux tensor)
+        gmod = (_POST_BWD[kind], pslope, y if kind != "none" else None)
+        pre = (L.XF_LRELU, cfg.pre_slope, None) if cfg.pre_slope is not None else (L.XF_NONE, 0.0, None)
+        s_kh, s_kw, s_cs, s_cd = cfg.wstr
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            dmod = (L.XF_MUL_DLRELU, cfg.pre_slope, x) if cfg.pre_slope is not None else (L.XF_NONE, 0.0, None)
+            if cfg.reflect:
+                # gradient w.r.t. the reflect-padded input, then fold the borders back
+                B, Hs, Ws, Cs = x.shape
+                gpad = torch.empty((B, Hs + 2 * cfg.ph, Ws + 2 * cfg.pw, Cs), dtype=torch.float32, device=x.device)
+                _launch_conv(gy, w, (s_kh, s_kw, s_cd, s_cs), None, None, gpad, cfg.KH, cfg.KW, cfg.sh, cfg.sw,
+                             cfg.dh, cfg.dw, 0, 0, False, True, src_xf=gmod)
+                gx = torch.empty_like(x)
+                L.call("msmc_reflect_pad_fold", L.ptr(gpad), L.ptr(gx), B, Hs, Ws, Cs, cfg.ph, cfg.pw)
+                if cfg.pre_slope is not None:
+                    gx = torch.where(x > 0, gx, gx * cfg.pre_slope)
+            else:
+                gx = torch.empty_like(x)
+                _launch_conv(gy, w, (s_kh, s_kw, s_cd, s_cs), None, None, gx, cfg.KH, cfg.KW, cfg.sh, cfg.sw,
+                             cfg.dh, cfg.dw, cfg.ph, cfg.pw, False, not cfg.transposed, src_xf=gmod, dst_xf=dmod)
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty_like(w) if w.is_contiguous() else torch.zeros_like(w)
+            want_b = ctx.has_bias and ctx.needs_input_grad[2]
+            if not cfg.transposed:
+                gb = torch.empty(cfg.Cd, dtype=torch.float32, device=x.device) if want_b else None
+                _launch_wgrad(x, gy, gw, cfg.wstr, gb, cfg.KH, cfg.KW, cfg.sh, cfg.sw, cfg.dh, cfg.dw, cfg.ph,
+                              cfg.pw, cfg.reflect, src_xf=pre, gout_xf=gmod)
+            else:
+                # roles swap: the op's output plays the gathered source, the op's input plays "gout"
+                _launch_wgrad(gy, x, gw, (s_kh, s_kw, s_cd, s_cs), None, cfg.KH, cfg.KW, cfg.sh, cfg.sw, cfg.dh,
+                              cfg.dw, cfg.ph, cfg.pw, False, src_xf=gmod, gout_xf=pre)
+                if want_b:
+                    gb = _post_grad(gy, y, cfg.post).sum(dim=(0, 1, 2))
+        elif ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = _post_grad(gy, y, cfg.post).sum(dim=(0, 1, 2))
+        gres = gy if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        return gx, gw, gb, gres, None
+
+
+def _post_grad(gy, y, post):
+    kind, slope = post
+    if kind == "relu":
+        return gy * (y > 0)
+    if kind == "tanh":
+        return gy * (1 - y * y)
+    if kind == "lrelu":
+        return torch.where(y > 0, gy, gy * slope)
+    return gy
+
+
+def conv_cl(x, w, bias=None, residual=None, *, kernel=(1, 1), stride=(1, 1), dilation=(1, 1), padding=(0, 0),
+            reflect=False, transposed=False, wstr=None, out_channels=None, pre_slope=None, post="none",
+            out_hw=None):
+    """Channels-last convolution-shaped contraction.  `w` is any tensor whose element for (kh, kw, cs, cd) sits
+    at the strides `wstr` (default: the GEMM layout [KH][KW][Cs][Cd], contiguous)."""
+    KH, KW = kernel
+    Cs = x.shape[-1]
+    if wstr is None:
+        Cd = w.shape[-1]
+        wstr = (KW * Cs * Cd, Cs * Cd, Cd, 1)
+    else:
+        Cd = out_channels
+    if isinstance(post, str):
+        post = (post, 0.0)
+    cfg = ConvCfg(KH, KW, stride[0], stride[1], dilation[0], dilation[1], padding[0], padding[1], bool(reflect),
+                  bool(transposed), tuple(int(s) for s in wstr), int(Cd), pre_slope, (post[0], float(post[1])),
+                  out_hw)
+    return _ConvFn.apply(x, w, bias, residual, cfg)
+
+
+def linear_cl(x, weight, bias=None, residual=None, post="none", pre_slope=None):
+    """x (..., Ci) @ weight(Co, Ci)^T + bias, weight consumed in torch's native nn.Linear / 1x1-conv layout."""
+    Ci = x.shape[-1]
+    Co = weight.shape[0]
+    lead = x.shape[:-1]
+    x4 = x.reshape(-1, 1, 1, Ci)
+    r4 = residual.reshape(-1, 1, 1, Co) if residual is not None else None
+    w2 = weight.reshape(Co, Ci)
+    y = conv_cl(x4, w2, bias, r4, wstr=(0, 0, 1, Ci), out_channels=Co, post=post, pre_slope=pre_slope)
+    return y.reshape(*lead, Co)
+
+
+# ------------------------------------------------------------------------------------------ weight prep
+class _PrepWeightFn(torch.autograd.Function):
+    """(v[, g]) -> GEMM-layout weight; weight_norm (dim=0) when g is given."""
+
+    @staticmethod
+    def forward(ctx, v, g, O, I, J, so, si, sj, out_shape):
+        v = v.contiguous()
+        w = torch.empty(out_shape, dtype=torch.float32, device=v.device)
+        inv = torch.empty(O, dtype=torch.float32, device=v.device) if g is not None else None
+        L.require_cuda(v, g)
+        L.call("msmc_weight_norm_fwd", L.ptr(v), L.ptr(g), L.ptr(w), L.ptr(inv), O, I, J,
+               C.c_int64(so), C.c_int64(si), C.c_int64(sj))
+        ctx.dims = (O, I, J, so, si, sj)
+        ctx.has_g = g is not None
+        ctx.save_for_backward(v, g, inv)
+        return w
+
+    @staticmethod
+    def backward(ctx, gw):
+        v, g, inv = ctx.saved_tensors
+        O, I, J, so, si, sj = ctx.dims
+        gw = gw.contiguous()
+        dv = torch.empty_like(v)
+        dg = torch.empty(O, dtype=torch.float32, device=v.device) if ctx.has_g else None
+        L.call("msmc_weight_norm_bwd", L.ptr(gw), C.c_int64(so), C.c_int64(si), C.c_int64(sj), L.ptr(v), L.ptr(g),
+               L.ptr(inv), L.ptr(dv), L.ptr(dg), O, I, J)
+        if ctx.has_g:
+            dg = dg.reshape(g.shape)
+        return dv, dg, None, None, None, None, None, None, None
+
+
+def prep_conv_weight(v, g=None, transposed=False):
+    """torch conv weight -> GEMM layout [KH][KW][Cs][Cd] (contiguous).
+    Conv:          v (Co, Ci, KH, KW) or (Co, Ci, K);  weight_norm over (Ci, K...) per Co.
+    ConvTranspose: v (Cin, Cout, K);                    weight_norm over (Cout, K) per Cin (torch dim=0)."""
+    if v.dim() == 3:
+        O, I, K = v.shape
+        KH, KW = 1, K
+    else:
+        O, I, KH, KW = v.shape
+    J = KH * KW
+    if not transposed:
+        # o = cd, i = cs:  offset = j*(I*O) + i*O + o
+        shape, so, si, sj = (KH, KW, I, O), 1, O, I * O
+    else:
+        # o = cs (Cin), i = cd (Cout): offset = j*(O*I) + o*I + i
+        shape, so, si, sj = (KH, KW, O, I), I, 1, O * I
+    return _PrepWeightFn.apply(v, g, O, I, J, so, si, sj, shape)
+
+
+# ------------------------------------------------------------------------------------------------ VQ
+class _VQFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, embed, n_heads, dim):
+        z2 = z.reshape(-1, n_heads * dim)
+        if z2.stride(-1) != 1:
+            z2 = z2.contiguous()
+        n_rows = z2.shape[0]
+        K = embed.shape[-1]
+        L.require_cuda(z2, embed)
+        q_raw = torch.empty((n_rows, n_heads * dim), dtype=torch.float32, device=z.device)
+        q_st = torch.empty_like(q_raw)
+        diff = torch.empty((n_rows, dim), dtype=torch.float32, device=z.device)
+        idx = torch.empty((n_rows, n_heads), dtype=torch.int64, device=z.device)
+        L.call("msmc_vq_search", L.ptr(z2), C.c_int64(z2.stride(0)), L.ptr(embed), L.ptr(q_raw), L.ptr(q_st),
+               L.ptr(diff), L.ptr(idx), n_rows, n_heads, dim, K)
+        ctx.save_for_backward(z2, q_raw)
+        ctx.hd = (n_heads, dim)
+        ctx.zshape = z.shape
+        lead = z.shape[:-1]
+        idx = idx.reshape(*lead, n_heads)
+        ctx.mark_non_differentiable(idx)
+        return q_st.reshape(*lead, n_heads * dim), diff.reshape(*lead, dim), idx
+
+    @staticmethod
+    def backward(ctx, g_q, g_diff, _g_idx):
+        z2, q_raw = ctx.saved_tensors
+        n_heads, dim = ctx.hd
+        n_rows = q_raw.shape[0]
+        zc = z2.contiguous()
+        gq = g_q.reshape(n_rows, -1).contiguous() if g_q is not None else None
+        gd = g_diff.reshape(n_rows, -1).contiguous() if g_diff is not None else None
+        gz = torch.empty_like(q_raw)
+        L.call("msmc_vq_backward", L.ptr(gq), L.ptr(gd), L.ptr(zc), L.ptr(q_raw), L.ptr(gz), n_rows, n_heads, dim)
+        return gz.reshape(ctx.zshape), None, None, None
+
+
+def vq_quantize(z, embed, n_heads, dim):
+    """z (..., n_heads*dim), embed (n_heads, dim, K) -> (quant_st, diff (..., dim), idx (..., n_heads) int64)"""
+    return _VQFn.apply(z, embed, n_heads, dim)
+
+
+def vq_ema_update(z, idx, lengths, embed, embed_avg, cluster_size, decay, eps):
+    """in-place EMA codebook update on the stacked buffers (n_heads, dim, K) / (n_heads, K)"""
+    n_heads, dim, K = embed.shape
+    B, t = z.shape[0], z.shape[1]
+    z2 = z.detach().reshape(B * t, n_heads * dim)
+    if z2.stride(-1) != 1:
+        z2 = z2.contiguous()
+    idx2 = idx.reshape(B * t, n_heads).contiguous()
+    lengths = lengths.to(device=z.device, dtype=torch.int32).contiguous()
+    L.require_cuda(z2, embed, embed_avg, cluster_size)
+    assert embed.is_contiguous() and embed_avg.is_contiguous() and cluster_size.is_contiguous()
+    L.call("msmc_vq_ema_update", L.ptr(z2), C.c_int64(z2.stride(0)), L.ptr(idx2), L.ptr(lengths), B, t, n_heads,
+           dim, K, C.c_float(decay), C.c_float(eps), L.ptr(cluster_size), L.ptr(embed_avg), L.ptr(embed))
+
+
+class _TripleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, embed, target, n_heads, dim, margin, reduce_mean):
+        p2 = pred.reshape(-1, n_heads * dim).contiguous()
+        n_rows = p2.shape[0]
+        K = embed.shape[-1]
+        t2 = target.reshape(n_rows, n_heads).contiguous()
+        loss = torch.empty((n_rows, n_heads), dtype=torch.float32, device=pred.device)
+        gp = torch.empty_like(p2)
+        L.require_cuda(p2, embed, t2)
+        L.call("msmc_vq_triple_loss", L.ptr(p2), C.c_int64(p2.stride(0)), L.ptr(embed), L.ptr(t2), L.ptr(loss),
+               L.ptr(gp), n_rows, n_heads, dim, K, C.c_float(margin), int(reduce_mean))
+        ctx.save_for_backward(gp)
+        ctx.pshape = pred.shape
+        return loss.sum(dim=1).reshape(pred.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, gl):
+        (gp,) = ctx.saved_tensors
+        g = gp * gl.reshape(-1, 1)
+        return g.reshape(ctx.pshape), None, None, None, None, None, None
+
+
+def vq_triple_loss(pred, embed, target, n_heads, dim, margin=1e-6, reduction="mean"):
+    return _TripleFn.apply(pred, embed, target, n_heads, dim, margin, reduction == "mean")
+
+
+# ------------------------------------------------------------------------------------------- dropout rng
+class DeviceRng:
+    """Device-resident 64-bit seed; `advance()` is a captured device op so graph replays draw fresh masks."""
+    _state = {}
+
+    @classmethod
+    def get(cls, device):
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        st = cls._state.get(key)
+        if st is None:
+            st = cls._state[key] = {"seed": torch.full((1,), int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF,
+                                                       dtype=torch.int64, device=device), "salt": 0}
+        return st
+
+    @classmethod
+    def next_salt(cls, device):
+        st = cls.get(device)
+        st["salt"] += 1
+        return st["seed"], st["salt"]
+
+    @classmethod
+    def advance(cls, device):
+        st = cls.get(device)
+        st["seed"].add_(0x632BE59BD9B4E019)
+        st["salt"] = 0
+
+
+# --------------------------------------------------------------------------------------------- attention
+class _AttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, lengths, n_head, d, inv_temp, drop_p):
+        qkv = qkv.contiguous()
+        B, t, _ = qkv.shape
+        out = torch.empty((B, t, n_head * d), dtype=torch.float32, device=qkv.device)
+        lse = torch.empty((n_head * B, t), dtype=torch.float32, device=qkv.device)
+        seed, salt = (None, 0)
+        if drop_p > 0:
+            seed, salt = DeviceRng.next_salt(qkv.device)
+        L.require_cuda(qkv, lengths)
+        L.call("msmc_attention_fwd", L.ptr(qkv), L.ptr(lengths), L.ptr(out), L.ptr(lse), B, t, n_head, d,
+               C.c_float(inv_temp), C.c_float(drop_p), L.ptr(seed), C.c_uint64(salt))
+        ctx.save_for_backward(qkv, lengths, out, lse, seed)
+        ctx.args = (n_head, d, inv_temp, drop_p, salt)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        qkv, lengths, out, lse, seed = ctx.saved_tensors
+        n_head, d, inv_temp, drop_p, salt = ctx.args
+        B, t, _ = qkv.shape
+        gout = gout.contiguous()
+        gqkv = torch.empty_like(qkv)
+        L.call("msmc_attention_bwd", L.ptr(qkv), L.ptr(lengths), L.ptr(out), L.ptr(lse), L.ptr(gout), L.ptr(gqkv),
+               B, t, n_head, d, C.c_float(inv_temp), C.c_float(drop_p), L.ptr(seed), C.c_uint64(salt))
+        return gqkv, None, None, None, None, None
+
+
+def attention(qkv, lengths, n_head, d, temperature, drop_p=0.0):
+    return _AttnFn.apply(qkv, lengths, n_head, d, 1.0 / float(temperature), float(drop_p))
+
+
+# --------------------------------------------------------------------------------------------- layernorm
+class _AddLNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, r, gamma, beta, lengths, eps, drop_p):
+        a = a.contiguous()
+        r = r.contiguous() if r is not None else None
+        B, t, Cn = a.shape
+        y = torch.empty_like(a)
+        xhat = torch.empty_like(a)
+        rstd = torch.empty(B * t, dtype=torch.float32, device=a.device)
+        seed, salt = (None, 0)
+        if drop_p > 0:
+            seed, salt = DeviceRng.next_salt(a.device)
+        L.require_cuda(a, r, gamma, beta)
+        L.call("msmc_add_layernorm_fwd", L.ptr(a), L.ptr(r), L.ptr(gamma), L.ptr(beta), L.ptr(lengths), L.ptr(y),
+               L.ptr(xhat), L.ptr(rstd), B, t, Cn, C.c_float(eps), C.c_float(drop_p), L.ptr(seed),
+               C.c_uint64(salt))
+        ctx.save_for_backward(xhat, rstd, gamma, lengths, seed)
+        ctx.args = (drop_p, salt, r is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xhat, rstd, gamma, lengths, seed = ctx.saved_tensors
+        drop_p, salt, has_r = ctx.args
+        B, t, Cn = xhat.shape
+        gy = gy.contiguous()
+        ga = torch.empty_like(xhat)
+        gr = torch.empty_like(xhat) if has_r else None
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        nbytes = L.load().msmc_add_layernorm_bwd_workspace(Cn)
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=xhat.device)
+        L.call("msmc_add_layernorm_bwd", L.ptr(gy), L.ptr(xhat), L.ptr(rstd), L.ptr(gamma), L.ptr(lengths),
+               L.ptr(ga), L.ptr(gr), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), B, t, Cn, C.c_float(drop_p),
+               L.ptr(seed), C.c_uint64(salt))
+        return ga, gr, dgamma, dbeta, None, None, None
+
+
+def add_layernorm(a, r, gamma, beta, lengths=None, eps=1e-5, drop_p=0.0):
+    """mask * LayerNorm(dropout(a) + r) over the last dim; a, r : (B, t, C); lengths int32 (B,) or None"""
+    return _AddLNFn.apply(a, r, gamma, beta, lengths, float(eps), float(drop_p))
+
+
+# --------------------------------------------------------------------------------------------- pointwise
+class _SpecMagFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, floor_, floor_add):
+        spec = spec.contiguous()
+        F2 = spec.shape[-1]
+        F = F2 // 2
+        rows = spec.numel() // F2
+        mag = torch.empty(spec.shape[:-1] + (F,), dtype=torch.float32, device=spec.device)
+        L.require_cuda(spec)
+        L.call("msmc_spec_magnitude_fwd", L.ptr(spec), L.ptr(mag), C.c_int64(rows), F, C.c_float(floor_),
+               int(floor_add))
+        ctx.save_for_backward(spec, mag)
+        ctx.args = (rows, F, floor_, floor_add)
+        return mag
+
+    @staticmethod
+    def backward(ctx, gmag):
+        spec, mag = ctx.saved_tensors
+        rows, F, floor_, floor_add = ctx.args
+        gmag = gmag.contiguous()
+        gspec = torch.empty_like(spec)
+        L.call("msmc_spec_magnitude_bwd", L.ptr(gmag), L.ptr(spec), L.ptr(mag), L.ptr(gspec), C.c_int64(rows), F,
+               C.c_float(floor_), int(floor_add))
+        return gspec, None, None
+
+
+def spec_magnitude(spec, floor_, floor_add=False):
+    """spec (..., 2F) = [re | im] -> (..., F)"""
+    return _SpecMagFn.apply(spec, float(floor_), bool(floor_add))
+
+
+class _MelDoubleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mel, ref_db, min_db):
+        mel = mel.contiguous()
+        out = torch.empty(mel.shape + (2,), dtype=torch.float32, device=mel.device)
+        L.require_cuda(mel)
+        L.call("msmc_mel_double_fwd", L.ptr(mel), L.ptr(out), C.c_int64(mel.numel()), C.c_float(ref_db),
+               C.c_float(min_db))
+        ctx.save_for_backward(mel)
+        ctx.args = (ref_db, min_db)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (mel,) = ctx.saved_tensors
+        gout = gout.contiguous()
+        gmel = torch.empty_like(mel)
+        L.call("msmc_mel_double_bwd", L.ptr(gout), L.ptr(mel), L.ptr(gmel), C.c_int64(mel.numel()),
+               C.c_float(ctx.args[0]), C.c_float(ctx.args[1]))
+        return gmel, None, None
+
+
+def mel_double(mel, ref_db=20.0, min_db=-100.0):
+    """mel (...,) -> (..., 2): [lin, clamp((20 log10(lin) - ref - min)/-min, 0, 1)]"""
+    return _MelDoubleFn.apply(mel, float(ref_db), float(min_db))
+
+
+class _LogClampFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, clip):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        L.require_cuda(x)
+        L.call("msmc_log_clamp_fwd", L.ptr(x), L.ptr(y), C.c_int64(x.numel()), C.c_float(clip))
+        ctx.save_for_backward(x)
+        ctx.clip = clip
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        L.call("msmc_log_clamp_bwd", L.ptr(gy), L.ptr(x), L.ptr(gx), C.c_int64(x.numel()), C.c_float(ctx.clip))
+        return gx, None
+
+
+def log_clamp(x, clip=1e-5):
+    return _LogClampFn.apply(x, float(clip))
+
+
+class _GatedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        C2 = x.shape[-1]
+        Cn = C2 // 2
+        rows = x.numel() // C2
+        y = torch.empty(x.shape[:-1] + (Cn,), dtype=torch.float32, device=x.device)
+        L.require_cuda(x)
+        L.call("msmc_gated_act_fwd", L.ptr(x), L.ptr(y), C.c_int64(rows), Cn)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        C2 = x.shape[-1]
+        L.call("msmc_gated_act_bwd", L.ptr(gy), L.ptr(x), L.ptr(gx), C.c_int64(x.numel() // C2), C2 // 2)
+        return gx
+
+
+def gated_act(x):
+    """x (..., 2C) -> tanh(x[..., :C]) * sigmoid(x[..., C:])   (channels-last form of modules.py:172-179)"""
+    return _GatedFn.apply(x)
