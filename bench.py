@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- mel-frames/s of one full MSMC-VQ-GAN GAN train step (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload ("config.workload"): the reference's VQGANTrainer.train_step after warm-up (trainers/msmctts_trainer.py:115-209)
+on the CSMSC yaml architecture with 256 codewords/head as BASELINE.json words it: autoencoder forward/backward
+(2-stage 4-head VQ + EMA, FFT encoders/decoder, HifiGAN generator on a 40-frame window), MelLoss, discriminator
+(UnivNet MRD + MPD) step, generator adversarial + feature-matching step, grad clip, AdamW on both -- B=16 per GPU,
+T=240, 80-dim mel, 24 kHz / hop 300 (the reference has no 22.05 kHz config), synthetic data,
+random-init weights, fp32.
+
+One JSON line on rank 0.  `value` = frames/s with inputs resident in HBM; `e2e` = the same through the public
+trainer API with per-step pinned-host -> device copies of the batch and a device -> host read of the loss;
+`roofline` = the dominant kernel family from a CUDA-event pass over instrumented steps; `cpu_baseline` = the CPU
+oracle port of the same step on the box's host cores (rank 0, N=1 only).
+`--impl reference` times that CPU port alone (the reference tree does not exist on the GPU box and its
+discriminator / MelLoss do not run unmodified on torch >= 2, SURVEY section 0 B4/B5: kind = "port").
+"""
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "msmc-tts_b200"))
+
+import torch  # noqa: E402
+
+B_PER_GPU, T_FRAMES, N_MELS, HOP, WIN_FRAMES, K_CODEWORDS = 16, 240, 80, 300, 40, 256
+CPU_SAMPLE_B = 4
+
+
+def load_cfg():
+    with open(os.path.join(ROOT, "tests", "golden", "csmsc_config.json")) as f:
+        cfg = json.load(f)
+    cfg["autoencoder"]["quantizer_config"]["embedding_sizes"] = K_CODEWORDS
+    return cfg
+
+
+def synth_batch(B, seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    mel = (1.5 * torch.randn(B, T_FRAMES, N_MELS, generator=g)).clamp_(-4, 4)
+    wav = (0.3 * torch.randn(B, T_FRAMES * HOP, 1, generator=g)).clamp_(-1, 1)
+    length = torch.full((B,), T_FRAMES, dtype=torch.int64)
+    batch = {"mel": mel, "mel_length": length, "wav": wav}
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    if device != "cpu":
+        batch = {k: v.to(device) for k, v in batch.items()}
+    return batch
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                p = json.load(f)
+            return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops_sustained",
+                                                                           p["bf16_tflops"])),
+                    "source": "measured (MEASURED_PEAKS.json)"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def build_cpu_trainer(cfg, seed=1234):
+    from oracle.train_step import OracleTrainer
+    sd_ae, sd_d = init_state_dicts(cfg, seed)
+    return OracleTrainer(sd_ae, sd_d, cfg, cfg["trainer"], cfg["optimizer"]["_default"], use_dropout=True)
+
+
+def init_state_dicts(cfg, seed):
+    """random-init weights of the CSMSC architecture (constructed on CPU; no kernels involved)"""
+    from msmctts.networks.hifigan import UnivNetDiscriminator
+    from msmctts.networks.vqgantts import MSMCVQGAN
+    from msmctts.utils.config import ConfigItem
+    torch.manual_seed(seed)
+    c = copy.deepcopy(cfg["autoencoder"])
+    ae = MSMCVQGAN(c["in_dim"], c["n_model_size"], ConfigItem(c["encoder_config"]),
+                   ConfigItem(c["quantizer_config"]), ConfigItem(c["frame_decoder_config"]),
+                   ConfigItem(c["decoder_config"]), c["pred_mel"])
+    d = UnivNetDiscriminator(ConfigItem(cfg["discriminator"]["mrd_config"]),
+                             ConfigItem(cfg["discriminator"]["mpd_config"]))
+    return ae.state_dict(), d.state_dict()
+
+
+def time_cpu_steps(cfg, steps, warmup, B):
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    tr = build_cpu_trainer(cfg)
+    batch = synth_batch(B, 99)
+    win = [(100, 100 + WIN_FRAMES)] * B
+    for _ in range(warmup):
+        tr.step(batch["mel"], batch["mel_length"], batch["wav"], win)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(batch["mel"], batch["mel_length"], batch["wav"], win)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return B * T_FRAMES / dt, dt, threads
+
+
+def run_reference(args, rank):
+    cfg = load_cfg()
+    if rank != 0:
+        return
+    # bounded: each step is a B=4 sample of the B=16 workload; cap the step count so the run stays within minutes
+    steps, warmup = min(args.steps, 12), min(args.warmup, 2)
+    value, dt, threads = time_cpu_steps(cfg, steps, warmup, CPU_SAMPLE_B)
+    sample = "full GAN train step on a B=%d slice of the B=%d batch, T=%d, %d timed steps after %d warm-up" % (
+        CPU_SAMPLE_B, B_PER_GPU, T_FRAMES, steps, warmup)
+    print(json.dumps({
+        "impl": "reference", "metric": "mel-frames/sec MSMC-VQ-GAN train step", "value": value,
+        "unit": "mel-frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "mel-frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(n):
+    return {"workload": "MSMC-VQ-GAN full GAN train step (AE fwd/bwd + MelLoss + UnivNet MRD/MPD D-step + G-step + "
+                        "AdamW), CSMSC yaml architecture, 2-stage 4-head VQ with %d codewords/head" % K_CODEWORDS,
+            "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * n, "mel_frames": T_FRAMES, "n_mels": N_MELS,
+            "sample_rate": 24000, "hop": HOP, "vocoder_window_frames": WIN_FRAMES, "parallelism": "dp%d" % n,
+            "l2_policy": "per-step working set (activations + 51M fp32 params, grads, Adam moments ~ 1.5 GB) "
+                         "exceeds the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def build_gpu_trainer(cfg, device, distributed, rank, world):
+    from msmctts.tasks.msmc_tts import MSMCTTS
+    from msmctts.trainers.msmctts_trainer import VQGANTrainer
+    from msmctts.utils.config import Config
+    ycfg = {"id": "bench", "task": {"_name": "MSMCTTS", "_mode": "train_autoencoder",
+                                    "autoencoder": dict(cfg["autoencoder"], _name="MSMCVQGAN"),
+                                    "discriminator": dict(cfg["discriminator"], _name="UnivNetDiscriminator")},
+            "trainer": dict(cfg["trainer"]), "optimizer": cfg["optimizer"],
+            "dataset": {"_name": "SyntheticMelDataset", "samplerate": 24000, "feature": ["mel", "wav"],
+                        "frameshift": [HOP, 1]},
+            "dataloader": {"batch_size": B_PER_GPU * world, "num_workers": 0}}
+    config = Config(ycfg)
+    torch.manual_seed(config.seed)
+    task = MSMCTTS(config, mode="train")
+    kwargs = config.trainer.to_dict()
+    kwargs.pop("_name")
+    kwargs["warmup_steps"] = 0      # bench the post-warm-up (GAN) step
+    trainer = VQGANTrainer(config, task, num_gpus=world, rank=rank, **kwargs)
+    trainer.build_optimizer()
+    task.train()
+    return trainer
+
+
+def vq_bandwidth(device, pk):
+    """VQ search kernel alone: at-config (both stages of one forward: N = 3840 + 960 rows) and an N sweep."""
+    from msmctts._b200 import functional as Fn
+    out = {}
+    heads, dim, K = 4, 64, K_CODEWORDS
+    embed = torch.randn(heads, dim, K, device=device)
+
+    def run(n, reps):
+        z = torch.randn(n, heads * dim, device=device)
+        for _ in range(3):
+            Fn.vq_quantize(z, embed, heads, dim)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            Fn.vq_quantize(z, embed, heads, dim)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        # algorithmic bytes: read z, codebooks; write quant_raw, quant_st, diff, idx
+        byt = n * heads * dim * 4 * 3 + n * dim * 4 + n * heads * 8 + heads * dim * K * 4
+        return byt / (ms * 1e-3) / 1e9, ms
+
+    g1, ms1 = run(3840, 50)
+    g2, ms2 = run(960, 50)
+    n_bytes = (3840 + 960) * (heads * dim * 4 * 3 + dim * 4 + heads * 8) + 2 * heads * dim * K * 4
+    out["at_config"] = {"rows": [3840, 960], "us": [ms1 * 1e3, ms2 * 1e3],
+                        "gbs": n_bytes / ((ms1 + ms2) * 1e-3) / 1e9,
+                        "frac_of_hbm_peak": n_bytes / ((ms1 + ms2) * 1e-3) / 1e9 / pk["hbm_gbs"],
+                        "note": "latency-bound: %.1f MB of traffic is < 3 us at HBM peak" % (n_bytes / 1e6)}
+    sweep = {}
+    for p in (12, 14, 16, 18, 20, 22):
+        g, ms = run(1 << p, 10 if p < 20 else 4)
+        sweep["2^%d" % p] = round(g, 1)
+    out["sweep_gbs"] = sweep
+    out["asymptote_frac_of_hbm_peak"] = max(sweep.values()) / pk["hbm_gbs"]
+    return out
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from msmctts._b200 import lib as L
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    L.load()
+    distributed = world > 1
+    if distributed and not dist.is_initialized():
+        dist.init_process_group("nccl")
+    cfg = load_cfg()
+    trainer = build_gpu_trainer(cfg, device, distributed, rank, world)
+    pk = peaks()
+    fixed_win = [(100, 100 + WIN_FRAMES)] * B_PER_GPU
+    dev_batch = synth_batch(B_PER_GPU, 1000 + rank, device=device)
+    host_batches = [synth_batch(B_PER_GPU, 2000 + rank * 16 + i, pin=True) for i in range(4)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident(i):
+        return trainer.train_step(dev_batch, iteration=10 + i, frame_windows=fixed_win)
+
+    def step_e2e(i):
+        hb = host_batches[i % len(host_batches)]
+        batch = {k: v.to(device, non_blocking=True) for k, v in hb.items()}
+        log = trainer.train_step(batch, iteration=10 + i, frame_windows=fixed_win)
+        return float(log["loss"]["g_loss"])          # device -> host read of the step's loss
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if distributed:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for i in range(max(3, args.warmup)):
+        step_resident(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = L.launch_count
+    ms_step = timed(step_resident, args.steps)
+    launches = (L.launch_count - l0) // args.steps
+    clocks = sampler.stop() if sampler else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    frames = B_PER_GPU * T_FRAMES * world
+    value = frames / (ms_step * 1e-3)
+    e2e_value = frames / (ms_e2e * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+
+    roof, families, vq = None, None, None
+    if rank == 0:
+        # ---- roofline pass: CUDA events around every C-ABI call of two more steps (same stream)
+        L.profile_begin()
+        for i in range(2):
+            step_resident(100 + i)
+        torch.cuda.synchronize()
+        prof = L.profile_end()
+        fam = {}
+        for name, meta, e0, e1 in prof:
+            f = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "calls": 0})
+            f["ms"] += e0.elapsed_time(e1)
+            f["calls"] += 1
+            if meta:
+                f["flops"] += meta["flops"]
+                f["bytes"] += meta["bytes"]
+        tot_ms = sum(f["ms"] for f in fam.values())
+        families = {k: {"ms_per_step": round(v["ms"] / 2, 3), "calls_per_step": v["calls"] // 2,
+                        "share": round(v["ms"] / tot_ms, 3)} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+        top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        tname, t = top
+        if t["flops"] > 0:
+            ach = t["flops"] / (t["ms"] * 1e-3) / 1e12
+            roof = {"kernel": tname, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"],
+                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
+                    "peak_source": pk["source"] + "; fp32 CUDA-core kernel measured against the dense bf16 tensor peak",
+                    "launches_per_step": t["calls"] // 2, "avg_launch_us": t["ms"] * 1e3 / t["calls"],
+                    "algorithmic_gflop_per_step": t["flops"] / 2 / 1e9,
+                    "share_of_kernel_time": round(t["ms"] / tot_ms, 3)}
+        else:
+            ach = t["bytes"] / (t["ms"] * 1e-3) / 1e9 if t["bytes"] else 0.0
+            roof = {"kernel": tname, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"]}
+        vq = vq_bandwidth(device, pk)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, threads = time_cpu_steps(cfg, 2, 1, CPU_SAMPLE_B)
+        cpu = {"value": v, "unit": "mel-frames/s", "cores": threads, "kind": "port",
+               "sample": "oracle port of the same full GAN step on a B=%d slice of the batch, 2 timed steps after 1 "
+                         "warm-up (%.1f s/step)" % (CPU_SAMPLE_B, dt)}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "mel-frames/sec MSMC-VQ-GAN train step", "value": value, "unit": "mel-frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "mel-frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+            "roofline": roof, "kernel_families": families, "vq_argmin": vq, "cpu_baseline": cpu}))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (the hot path has no CPU fallback)")
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

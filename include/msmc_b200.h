@@ -136,6 +136,8 @@ int msmc_add_layernorm_fwd(const float* a, const float* r, const float* gamma, c
                            const int32_t* lengths, float* y, float* xhat, float* rstd,
                            int32_t B, int32_t t, int32_t C, float eps, float drop_p,
                            const uint64_t* seed, uint64_t call_salt, void* stream);
+/* bytes of `workspace` msmc_add_layernorm_bwd needs (per-CTA partial dgamma/dbeta rows) */
+int64_t msmc_add_layernorm_bwd_workspace(int32_t C);
 int msmc_add_layernorm_bwd(const float* gy, const float* xhat, const float* rstd, const float* gamma,
                            const int32_t* lengths, float* ga, float* gr, float* dgamma, float* dbeta,
                            float* workspace, int32_t B, int32_t t, int32_t C, float drop_p,

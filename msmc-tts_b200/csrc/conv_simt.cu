@@ -13,7 +13,7 @@ namespace {
 constexpr int BM = 128;   // rows of the output tile held by one CTA
 constexpr int BK = 16;    // reduction chunk
 constexpr int NTHREADS = 256;
-constexpr int MAX_TAPS_TABLE = 1024;
+constexpr int MAX_TAPS_TABLE = 4096;
 
 struct ConvArgs {
   msmc_conv_geom g;
@@ -93,18 +93,26 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const ConvArgs a) {
   int ntaps = g.KH * g.KW;
   if (g.transposed) {
     if (tid == 0) {
+      // valid taps of a phase form an arithmetic progression with period s / gcd(d, s) along each axis
+      auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+      auto first_valid = [](int r, int p, int d, int s, int period, int K) {
+        for (int k = 0; k < period && k < K; ++k) {
+          int t = r + p - k * d;
+          if (((t % s) + s) % s == 0) return k;
+        }
+        return K;  // none
+      };
+      const int per_h = g.sh / gcd(g.dh % g.sh == 0 ? g.sh : g.dh % g.sh, g.sh);
+      const int per_w = g.sw / gcd(g.dw % g.sw == 0 ? g.sw : g.dw % g.sw, g.sw);
+      const int kh0 = first_valid(rh, g.ph, g.dh, g.sh, per_h, g.KH);
+      const int kw0 = first_valid(rw, g.pw, g.dw, g.sw, per_w, g.KW);
       int c = 0;
-      for (int kh = 0; kh < g.KH; ++kh) {
-        int th = rh + g.ph - kh * g.dh;
-        if (((th % g.sh) + g.sh) % g.sh != 0) continue;
-        for (int kw = 0; kw < g.KW; ++kw) {
-          int tw = rw + g.pw - kw * g.dw;
-          if (((tw % g.sw) + g.sw) % g.sw != 0) continue;
+      for (int kh = kh0; kh < g.KH; kh += per_h)
+        for (int kw = kw0; kw < g.KW; kw += per_w) {
           tap_kh[c] = (short)kh;
           tap_kw[c] = (short)kw;
           ++c;
         }
-      }
       s_ntaps = c;
     }
     __syncthreads();

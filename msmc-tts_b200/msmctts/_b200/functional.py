@@ -64,8 +64,14 @@ def _launch_conv(src, w, wstr, bias, residual, dst, KH, KW, sh, sw, dh, dw, ph, 
     g.src_xf, g.src_slope = src_xf[0], float(src_xf[1])
     g.dst_xf, g.dst_slope = dst_xf[0], float(dst_xf[1])
     L.require_cuda(src, w, dst)
+    meta = None
+    if L._profile is not None:
+        pos = B * (Hs * Ws if transposed else Hd * Wd)
+        meta = {"flops": 2.0 * pos * KH * KW * Cs * Cd,
+                "bytes": 4.0 * (src.numel() + dst.numel() + KH * KW * Cs * Cd + (res.numel() if res is not None else 0)),
+                "shape": "B%d %dx%d C%d->%d k%dx%d s%d%s" % (B, Hs, Ws, Cs, Cd, KH, KW, sw, "T" if transposed else "")}
     L.call("msmc_conv_forward", C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(w), L.ptr(bias), L.ptr(res),
-           L.ptr(daux), L.ptr(dst))
+           L.ptr(daux), L.ptr(dst), meta=meta)
     return dst
 
 
@@ -92,8 +98,13 @@ def _launch_wgrad(src, gout, dw, wstr, dbias, KH, KW, sh, sw, dh, dw_, ph, pw, r
     lib = L.load()
     nbytes = lib.msmc_conv_wgrad_workspace(C.byref(g))
     ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=src.device)
+    meta = None
+    if L._profile is not None:
+        meta = {"flops": 2.0 * B * Hd * Wd * KH * KW * Cs * Cd,
+                "bytes": 4.0 * (src.numel() + gout.numel() + KH * KW * Cs * Cd),
+                "shape": "wgrad B%d %dx%d C%d->%d k%dx%d" % (B, Hs, Ws, Cs, Cd, KH, KW)}
     L.call("msmc_conv_wgrad", C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(gout), L.ptr(daux), L.ptr(dw),
-           L.ptr(dbias), L.ptr(ws), C.c_int64(nbytes))
+           L.ptr(dbias), L.ptr(ws), C.c_int64(nbytes), meta=meta)
 
 
 # post = (kind, slope): result transform fused in the conv epilogue, and the operand modifier its backward needs

@@ -1,0 +1,119 @@
+"""Parameter containers whose names/shapes match torch.nn (and old-style torch.nn.utils.weight_norm) modules so the
+reference's checkpoints load unchanged, with forwards that run on the channels-last sm_100a kernels."""
+import math
+
+import torch
+from torch import nn
+
+from . import functional as Fn
+
+
+def _conv_init(weight, bias, fan_in):
+    nn.init.kaiming_uniform_(weight, a=math.sqrt(5))
+    if bias is not None and fan_in > 0:
+        bound = 1 / math.sqrt(fan_in)
+        nn.init.uniform_(bias, -bound, bound)
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+class Linear(nn.Linear):
+    """nn.Linear parameters; forward = msmc_conv_forward with the weight consumed in its native (Co, Ci) layout."""
+
+    def forward(self, x, post="none", residual=None):
+        return Fn.linear_cl(x, self.weight, self.bias, residual=residual, post=post)
+
+
+class Conv1d(nn.Module):
+    """nn.Conv1d parameters `weight` (Co, Ci, K), `bias`; x and y are (B, L, C)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, kernel_size))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        _conv_init(self.weight, self.bias, in_channels * kernel_size)
+
+    def gemm_weight(self):
+        return self.weight, None
+
+    def forward(self, x, pre_slope=None, post="none", residual=None):
+        B, L, _ = x.shape
+        v, g = self.gemm_weight()
+        if self.kernel_size == 1 and g is None:
+            return Fn.linear_cl(x, v, self.bias, residual=residual, post=post, pre_slope=pre_slope)
+        w = Fn.prep_conv_weight(v, g)
+        r4 = residual.unsqueeze(1) if residual is not None else None
+        y = Fn.conv_cl(x.unsqueeze(1), w, self.bias, r4, kernel=(1, self.kernel_size), stride=(1, self.stride),
+                       dilation=(1, self.dilation), padding=(0, self.padding), pre_slope=pre_slope, post=post)
+        return y.squeeze(1)
+
+
+class WNConv1d(Conv1d):
+    """weight_norm(nn.Conv1d): parameters `bias`, `weight_g` (Co,1,1), `weight_v` (Co,Ci,K) in that order."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        v = self.weight.data
+        del self.weight
+        self.weight_g = nn.Parameter(v.norm(2, dim=(1, 2), keepdim=True))
+        self.weight_v = nn.Parameter(v)
+
+    def gemm_weight(self):
+        return self.weight_v, self.weight_g
+
+
+class WNConvTranspose1d(nn.Module):
+    """weight_norm(nn.ConvTranspose1d): `weight_v` (Cin, Cout, K), `weight_g` (Cin,1,1) (torch's dim=0)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding=0):
+        super().__init__()
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+        v = torch.empty(in_channels, out_channels, kernel_size)
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        _conv_init(v, self.bias, out_channels * kernel_size)
+        self.weight_g = nn.Parameter(v.norm(2, dim=(1, 2), keepdim=True))
+        self.weight_v = nn.Parameter(v)
+
+    def forward(self, x, pre_slope=None):
+        w = Fn.prep_conv_weight(self.weight_v, self.weight_g, transposed=True)
+        y = Fn.conv_cl(x.unsqueeze(1), w, self.bias, kernel=(1, self.kernel_size), stride=(1, self.stride),
+                       padding=(0, self.padding), transposed=True, pre_slope=pre_slope)
+        return y.squeeze(1)
+
+
+class WNConv2d(nn.Module):
+    """weight_norm(nn.Conv2d): `bias`, `weight_g` (Co,1,1,1), `weight_v` (Co,Ci,KH,KW); x is (B, H, W, C).
+    swap_hw=True runs on a tensor whose two spatial axes are exchanged w.r.t. the reference's (taps transposed)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, reflect=False, swap_hw=False):
+        super().__init__()
+        self.kernel_size, self.stride, self.padding = _pair(kernel_size), _pair(stride), _pair(padding)
+        self.reflect, self.swap_hw = reflect, swap_hw
+        self.in_channels, self.out_channels = in_channels, out_channels
+        v = torch.empty(out_channels, in_channels, *self.kernel_size)
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        _conv_init(v, self.bias, in_channels * self.kernel_size[0] * self.kernel_size[1])
+        self.weight_g = nn.Parameter(v.norm(2, dim=(1, 2, 3), keepdim=True))
+        self.weight_v = nn.Parameter(v)
+
+    def forward(self, x, pre_slope=None, post="none"):
+        KH, KW = self.kernel_size
+        Ci, Co = self.in_channels, self.out_channels
+        w = Fn.prep_conv_weight(self.weight_v, self.weight_g)       # [kh][kw][ci][co], reference tap order
+        if not self.swap_hw:
+            return Fn.conv_cl(x, w, self.bias, kernel=(KH, KW), stride=self.stride, padding=self.padding,
+                              reflect=self.reflect, pre_slope=pre_slope, post=post)
+        return Fn.conv_cl(x, w, self.bias, kernel=(KW, KH), stride=self.stride[::-1], padding=self.padding[::-1],
+                          reflect=self.reflect, pre_slope=pre_slope, post=post,
+                          wstr=(Ci * Co, KW * Ci * Co, Co, 1), out_channels=Co)
+
+
+class LayerNormParams(nn.LayerNorm):
+    """nn.LayerNorm parameters; the math runs fused in add_layernorm (residual + dropout + LN + pad mask)."""
+
+    def forward(self, a, r=None, lengths=None, drop_p=0.0):
+        return Fn.add_layernorm(a, r, self.weight, self.bias, lengths, self.eps, drop_p)

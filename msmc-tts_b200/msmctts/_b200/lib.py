@@ -67,7 +67,11 @@ SIGNATURES = {
 
 _STATUS = {1: "MSMC_ERR_BAD_ARG", 2: "MSMC_ERR_LAUNCH", 3: "MSMC_ERR_UNSUPPORTED"}
 _lib = None
-launch_count = 0  # number of C-ABI compute calls issued (bench.py reports kernels launched)
+# kernels each entry point launches (bench.py's `gpu_launches` is the sum over the timed region)
+KERNELS_PER_CALL = {"msmc_conv_wgrad": 2, "msmc_vq_ema_update": 2, "msmc_attention_bwd": 2,
+                    "msmc_add_layernorm_bwd": 2}
+launch_count = 0   # kernels launched through the C-ABI so far
+_profile = None    # when a list: (name, meta, start_event, end_event) per call, for bench.py's roofline pass
 
 
 class MsmcError(RuntimeError):
@@ -102,12 +106,30 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-def call(name, *args):
+def profile_begin():
+    global _profile
+    _profile = []
+
+
+def profile_end():
+    global _profile
+    out, _profile = _profile, None
+    return out
+
+
+def call(name, *args, meta=None):
     """Invoke a status-returning entry point on the current stream."""
     global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args, stream_ptr())
-    launch_count += 1
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream_ptr())
+        e1.record()
+        _profile.append((name, meta, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args, stream_ptr())
+    launch_count += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise MsmcError("%s failed: %s" % (name, _STATUS.get(rc, rc)))
 

@@ -1,0 +1,200 @@
+"""GAN / predictor train steps driving the sm_100a network kernels (reference trainers/msmctts_trainer.py:12-294).
+
+Same losses and update order as VQGANTrainer.train_step (:115-209): VQ + frame + MelLoss, discriminator step on
+(fake.detach(), real), then generator step with adversarial + feature-matching terms, gradient clipping, AdamW.
+Host-side differences only: no `.item()` host syncs inside the step (the reference has 8 explicit ones plus ~265
+implicit) -- losses are returned as 0-dim device tensors and read when they are logged; the window
+gather is tensor arithmetic instead of per-sample Python slicing, so the step is CUDA-graph capturable.
+"""
+import random
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from msmctts.tasks import load_model
+from msmctts.utils.utils import get_mask_from_lengths
+from .base_trainer import BaseTrainer
+from .criterions.stft_loss import MelLoss
+
+
+class DurationLoss(nn.Module):
+    def __init__(self, lambda_dur=1):
+        super().__init__()
+        self.lambda_dur = lambda_dur
+
+    def forward(self, outputs, targets):
+        dur_target = targets["dur"].float()
+        dur_length = targets["text_length"]
+        loss = F.mse_loss(outputs["duration"], dur_target, reduction="none")
+        loss = loss.masked_fill(get_mask_from_lengths(dur_length, loss.shape[1]), 0)
+        dur_loss = loss.sum() / dur_length.sum()
+        return {"total_loss": self.lambda_dur * dur_loss, "dur_loss": dur_loss}
+
+
+class QuantizerLoss(nn.Module):
+    """masked commitment loss per stage + weighted prior-prediction loss (reference :39-71)"""
+
+    def __init__(self, lambda_vq=1, lambda_pr=1):
+        super().__init__()
+        self.lambda_vq, self.lambda_pr = lambda_vq, lambda_pr
+
+    def forward(self, outputs):
+        loss = {"vq_loss": 0}
+        latent_losses = outputs["encoder_diffs"]
+        if not isinstance(latent_losses, (tuple, list)):
+            latent_losses = [latent_losses]
+        for i, term in enumerate(latent_losses):
+            length = outputs["encoder_lengths"][i]
+            mask = get_mask_from_lengths(length, term.shape[1])
+            term = term.masked_fill(mask.unsqueeze(-1), 0)
+            term = term.sum() / length.sum() / term.shape[2]
+            loss["latent_loss_{}_{}".format(i, 0)] = term
+            loss["vq_loss"] = loss["vq_loss"] + self.lambda_vq * term
+        dd = outputs.get("decoder_diffs")
+        if isinstance(dd, dict):
+            dd = dict(dd)
+            loss["vq_loss"] = loss["vq_loss"] + self.lambda_pr * dd.pop("total_loss")
+            loss.update(dd)
+        return loss
+
+
+class VQGANTrainer(BaseTrainer):
+    def __init__(self, config, model, num_gpus=1, rank=0, warmup_steps=0, lambda_frame=1.0,
+                 eval_inteval_iters=1000, grad_clip_thresh=1.0, sample_lengths=24000, lambda_vq=1, lambda_pr=1,
+                 lambda_fm=2, lambda_stft=45, stft_loss_func="mel_loss", stft_loss_config=None):
+        super().__init__(config, model, num_gpus, rank)
+        self.lambda_frame, self.warmup_steps = lambda_frame, warmup_steps
+        self.frameshift = self.config.dataset.frameshift[self.config.dataset.feature.index("mel")]
+        self.frame_lengths = -1 if sample_lengths == -1 else sample_lengths // self.frameshift
+        self.grad_clip_thresh = grad_clip_thresh
+        self.vq_criterion = QuantizerLoss(lambda_vq=lambda_vq, lambda_pr=lambda_pr)
+        self.sample_lengths, self.lambda_fm, self.lambda_stft = sample_lengths, lambda_fm, lambda_stft
+        if stft_loss_func != "mel_loss":
+            raise NotImplementedError("only the default 'mel_loss' criterion is built on the B200 path")
+        sr = config.dataset.samplerate
+        kwargs = dict(sample_rate=sr, win_size=sr // 20, hop_size=sr // 80, num_mels=128)
+        kwargs["fft_size"] = 2048 if kwargs["win_size"] > 1024 else 1024
+        if stft_loss_config is not None:
+            kwargs.update(stft_loss_config)
+        self.stft_criterion = MelLoss(**kwargs)
+        if next(model.parameters()).is_cuda:
+            self.stft_criterion = self.stft_criterion.cuda()
+
+    # ------------------------------------------------------------------ window selection (reference :211-219)
+    def random_select(self, mel_length):
+        lengths = mel_length.tolist() if torch.is_tensor(mel_length) else list(mel_length)
+        frame_windows, sample_windows = [], []
+        for n in lengths:
+            start = random.randrange(max(1, int(n) - self.frame_lengths))
+            end = start + self.frame_lengths
+            frame_windows.append((start, end))
+            sample_windows.append((start * self.frameshift, end * self.frameshift))
+        return frame_windows, sample_windows
+
+    @staticmethod
+    def gather_windows(x, starts, length):
+        """x (B, T, ...), starts (B,) device int64 -> (B, length, ...) without host-side slicing"""
+        idx = starts.view(-1, 1) + torch.arange(length, device=x.device).view(1, -1)
+        idx = idx.view(idx.shape + (1,) * (x.dim() - 2)).expand(-1, -1, *x.shape[2:])
+        return torch.gather(x, 1, idx)
+
+    # ------------------------------------------------------------------------------------------ the step
+    def train_step(self, batch, iteration, frame_windows=None):
+        mel, mel_length = batch["mel"], batch["mel_length"]
+        wav = batch["wav"]
+        if iteration < self.warmup_steps:
+            return self._step(mel, mel_length, None, None, warmup=True, gan=False)
+        if frame_windows is None:
+            frame_windows, _ = self.random_select(mel_length.cpu())
+        starts = torch.as_tensor([w[0] for w in frame_windows], device=mel.device, dtype=torch.int64)
+        return self._step(mel, mel_length, wav, starts, warmup=False, gan=iteration > self.warmup_steps)
+
+    def _step(self, mel, mel_length, wav, starts, warmup, gan):
+        """sync-free body; everything inside is device work (graph-capturable)"""
+        losses = {}
+        ae, disc = self.model.autoencoder, getattr(self.model, "discriminator", None)
+        if warmup:
+            output = ae(mel, mel_length, warmup=True)
+        else:
+            target = self.gather_windows(wav, starts * self.frameshift, self.frame_lengths * self.frameshift)
+            output = ae(mel, mel_length, warmup=False, window=(starts, self.frame_lengths))
+        vq = self.vq_criterion(output)
+        losses.update(vq)
+        g_loss = vq["vq_loss"]
+        if "mel_outputs" in output:
+            ml = F.mse_loss(mel, output["mel_outputs"], reduction="none")
+            ml = ml.masked_fill(get_mask_from_lengths(mel_length, mel.shape[1]).unsqueeze(-1), 0)
+            ml = ml.sum() / mel_length.sum() / ml.shape[2]
+            losses["frame_loss"] = ml
+            g_loss = g_loss + self.lambda_frame * ml
+        if gan:
+            predict = output["decoder_outputs"].squeeze(-1)
+            target = target.reshape(predict.shape)
+            stft_loss = self.stft_criterion(predict, target)
+            losses["stft_loss"] = stft_loss
+            g_loss = g_loss + self.lambda_stft * stft_loss
+            # ---- discriminator step (reference :162-179)
+            fake_scores, _ = disc(predict.detach())
+            real_scores, _ = disc(target)
+            d_real = sum(F.mse_loss(s, torch.ones_like(s)) for s in real_scores)
+            d_fake = sum(F.mse_loss(s, torch.zeros_like(s)) for s in fake_scores)
+            d_loss = d_real + d_fake
+            losses.update(d_loss_real=d_real, d_loss_fake=d_fake, d_loss=d_loss)
+            self.optimizer.zero_grad(["discriminator"])
+            self.backward(d_loss, "discriminator")
+            self.optimizer.step(["discriminator"])
+            # ---- generator step (reference :182-201): D has already been updated, both passes are recomputed
+            fake_scores, fake_feats = disc(predict)
+            _, real_feats = disc(target)
+            adv = sum(F.mse_loss(s, torch.ones_like(s)) for s in fake_scores)
+            fm = sum(F.l1_loss(a, b) for fa, fb in zip(fake_feats, real_feats) for a, b in zip(fa, fb))
+            scale = self.lambda_fm if self.lambda_fm != "auto" else (g_loss / fm).detach()
+            adv_loss = adv + fm * scale
+            g_loss = g_loss + adv_loss
+            losses.update(fm_loss=fm, adv_loss=adv_loss, g_loss=g_loss)
+        self.optimizer.zero_grad(["autoencoder"])
+        self.backward(g_loss, "autoencoder")
+        nn.utils.clip_grad_norm_(self.model.autoencoder.parameters(), self.grad_clip_thresh)
+        self.optimizer.step(["autoencoder"])
+        return {"loss": {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}}
+
+
+class PredictorTrainer(BaseTrainer):
+    """multi-stage predictor training against a frozen autoencoder (reference :222-295)"""
+
+    def __init__(self, config, model, num_gpus=1, rank=0, grad_clip_thresh=1.0, eval_inteval_iters=1000,
+                 training_methods=["mse"], loss_weights=[1.0], lambda_dur=1.0):
+        super().__init__(config, model, num_gpus, rank)
+        self.training_methods, self.loss_weights = training_methods, loss_weights
+        self.grad_clip_thresh = grad_clip_thresh
+        self.dur_loss = DurationLoss(lambda_dur)
+
+    def train_step(self, batch, iteration):
+        batch = dict(batch)
+        if not hasattr(self, "autoencoder"):
+            self.build_autoencoder()
+        self.autoencoder.eval()
+        with torch.no_grad():
+            qs = self.autoencoder.analysis(batch.pop("mel"), batch.pop("mel_length").int())
+            batch["feat"], batch["feat_length"] = qs["quantizer_outputs"], qs["quantizer_lengths"]
+        output = self.model.predictor(**batch)
+        emb = self.autoencoder.compute_embedding_loss(output["feat"], output["feat_length"], qs,
+                                                      methods=self.training_methods, loss_weights=self.loss_weights)
+        losses = {"total_loss": emb.pop("total_loss")}
+        losses.update(emb)
+        dur = self.dur_loss(output, batch)
+        losses["total_loss"] = losses["total_loss"] + dur.pop("total_loss")
+        losses.update(dur)
+        self.optimizer.zero_grad(["predictor"])
+        self.backward(losses["total_loss"], "predictor")
+        if self.grad_clip_thresh is not None:
+            losses["grad_norm"] = nn.utils.clip_grad_norm_(self.model.predictor.parameters(), self.grad_clip_thresh)
+        self.optimizer.step(["predictor"])
+        return {"loss": {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}}
+
+    def build_autoencoder(self, autoencoder=None):
+        if autoencoder is None:
+            cfg = self.config.task.autoencoder
+            autoencoder = load_model("autoencoder", cfg._checkpoint, cfg.get("_config"))
+        self.autoencoder = autoencoder.cuda() if torch.cuda.is_available() else autoencoder

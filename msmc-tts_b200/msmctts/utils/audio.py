@@ -1,0 +1,100 @@
+"""Spectral front end of the multi-resolution discriminator on the sm_100a kernels
+(reference utils/audio.py: create_fb_matrix :30-84, MelScale :314-376, TorchSTFT :379-426).
+
+The windowed, normalised, centre-padded (reflect) STFT is one msmc_conv_forward over the raw waveform with a fixed
+(n_fft x 2F) cos|-sin basis (Cs = 1, stride = hop); magnitude, mel projection and the 'double' lin/log stacking
+follow as point-wise kernels + one GEMM.  Output layout is (B, frames, F, channels) -- the reference's
+(B, channels, F, frames) with the spatial axes exchanged; `transform` returns the reference layout for API parity.
+"""
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from msmctts._b200 import functional as Fn
+
+
+def create_fb_matrix(n_freqs, f_min, f_max, n_mels, sample_rate, norm=None):
+    """HTK triangular filterbank clamped to [1e-6, 1] (reference audio.py:30-84, norm=None)"""
+    if norm is not None:
+        raise ValueError("only norm=None is used on this path")
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + (f_min / 700.0))
+    m_max = 2595.0 * math.log10(1.0 + (f_max / 700.0))
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    fb = torch.min((-1.0 * slopes[:, :-2]) / f_diff[:-1], slopes[:, 2:] / f_diff[1:])
+    return torch.clamp(fb, 1e-6, 1)
+
+
+def dft_basis(n_fft, win_length, normalized, dtype=torch.float32):
+    """(win_length, 2F) basis [cos | -sin] * hann(win_length), for the window's non-zero span only.
+    torch.stft centres a short window inside n_fft (left pad (n_fft - win)/2); returns (basis, left)."""
+    left = (n_fft - win_length) // 2
+    k = np.arange(win_length, dtype=np.float64) + left
+    f = np.arange(n_fft // 2 + 1, dtype=np.float64)
+    ang = 2.0 * np.pi * np.outer(k, f) / n_fft
+    win = torch.hann_window(win_length, dtype=torch.float64).numpy()     # periodic, like the reference
+    scale = (1.0 / math.sqrt(n_fft)) if normalized else 1.0
+    basis = np.concatenate([np.cos(ang), -np.sin(ang)], axis=1) * win[:, None] * scale
+    return torch.from_numpy(basis).to(dtype), left
+
+
+class MelScale(nn.Module):
+    def __init__(self, n_mels=128, sample_rate=24000, f_min=0.0, f_max=None, n_stft=None):
+        super().__init__()
+        self.n_mels, self.sample_rate = n_mels, sample_rate
+        self.f_max = f_max if f_max is not None else float(sample_rate // 2)
+        self.f_min = f_min
+        fb = create_fb_matrix(n_stft, self.f_min, self.f_max, n_mels, sample_rate) if n_stft else torch.empty(0)
+        self.register_buffer("fb", fb, persistent=False)
+
+    def forward_cl(self, mag):
+        """mag (B, frames, F) -> (B, frames, n_mels)"""
+        B, T, Fq = mag.shape
+        y = Fn.conv_cl(mag.reshape(B * T, 1, 1, Fq), self.fb, wstr=(0, 0, self.n_mels, 1),
+                       out_channels=self.n_mels)
+        return y.reshape(B, T, self.n_mels)
+
+
+class TorchSTFT(nn.Module):
+    def __init__(self, fft_size, hop_size, win_size, normalized=False, domain="linear", mel_scale=False,
+                 sample_rate=24000, ref_level_db=20, min_level_db=-100):
+        super().__init__()
+        self.fft_size, self.hop_size, self.win_size = fft_size, hop_size, win_size
+        self.ref_level_db, self.min_level_db = ref_level_db, min_level_db
+        self.normalized, self.domain = normalized, domain
+        self.n_freq = fft_size // 2 + 1
+        basis, self.left = dft_basis(fft_size, win_size, normalized)
+        self.register_buffer("basis", basis, persistent=False)          # (win, 2F): GEMM layout [tap][1][2F]
+        self.mel_scale = MelScale(self.n_freq, sample_rate, n_stft=self.n_freq) if mel_scale else None
+
+    def spectrum_cl(self, x, center=True, pad=None):
+        """x (B, L) -> (B, frames, 2F) = [re | im]"""
+        B, L = x.shape
+        p = (self.fft_size // 2 if center else 0) if pad is None else pad
+        p = p - self.left
+        y = Fn.conv_cl(x.reshape(B, 1, L, 1), self.basis, kernel=(1, self.win_size), stride=(1, self.hop_size),
+                       padding=(0, p), reflect=True, wstr=(0, 2 * self.n_freq, 2 * self.n_freq, 1),
+                       out_channels=2 * self.n_freq)
+        return y.squeeze(1)
+
+    def transform_cl(self, x):
+        """x (B, L) -> (B, frames, F, C) with C = 2 ('double': lin, log), else 1"""
+        mag = Fn.spec_magnitude(self.spectrum_cl(x), 1e-7, False)
+        if self.mel_scale is not None:
+            mag = self.mel_scale.forward_cl(mag)
+        if self.domain == "double":
+            return Fn.mel_double(mag, self.ref_level_db, self.min_level_db)
+        if self.domain == "linear":
+            return mag.unsqueeze(-1)
+        return Fn.mel_double(mag, self.ref_level_db, self.min_level_db)[..., 1:]
+
+    def transform(self, x):
+        """reference layout: (B, 2F | F, frames), phase is not computed on this path (unused by the discriminator)"""
+        y = self.transform_cl(x)                      # (B, frames, F, C)
+        B, T, Fq, Cn = y.shape
+        return y.permute(0, 3, 2, 1).reshape(B, Cn * Fq, T), None

@@ -232,6 +232,15 @@ def gen_keys():
                discriminator_params=sum(p.numel() for p in dd.parameters()))
     with open(os.path.join(OUT, "csmsc_state_dict_keys.json"), "w") as f:
         json.dump(out, f)
+    ae_cfg_plain = {k: v for k, v in cfg.task.autoencoder.to_dict().items() if not k.startswith('_')}
+    d_cfg_plain = {k: v for k, v in cfg.task.discriminator.to_dict().items() if not k.startswith('_')}
+    # the yaml blocks themselves (examples/csmsc/configs/msmc_vq_gan.yaml:10-67, 89-98), for tests and bench.py
+    with open(os.path.join(OUT, "csmsc_config.json"), "w") as f:
+        json.dump(dict(autoencoder=ae_cfg_plain, discriminator=d_cfg_plain,
+                       trainer=cfg.trainer.to_dict(), optimizer=cfg.optimizer.to_dict(),
+                       dataset=dict(samplerate=cfg.dataset.samplerate, frameshift=cfg.dataset.frameshift,
+                                    feature=cfg.dataset.feature, padding_value=cfg.dataset.padding_value)),
+                  f, indent=1)
     print("csmsc keys: ae %d tensors %.2fM params, d %d tensors %.2fM params" % (
         len(out["autoencoder"]), out["autoencoder_params"] / 1e6, len(out["discriminator"]),
         out["discriminator_params"] / 1e6))

@@ -1,0 +1,50 @@
+"""CPU restatement of one full VQGANTrainer.train_step (reference trainers/msmctts_trainer.py:115-209) on top of
+oracle/ref_modules.py: forward, D step, G step, clip, AdamW.  TEST INFRASTRUCTURE / CPU BASELINE ONLY.
+
+Used by bench.py (`cpu_baseline`, `--impl reference`: the reference tree is absent on the GPU box and its
+discriminator / MelLoss do not run unmodified on torch>=2 -- SURVEY section 0, B4/B5 -- so the timed CPU arm is this
+port, kind "port") and by tests/ for whole-step parity.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ref_modules as O
+
+
+class OracleTrainer(object):
+    def __init__(self, sd_ae, sd_d, cfg, tcfg, ocfg, use_dropout=True):
+        """sd_* : state dicts keyed like the reference's; cfg = {'autoencoder':..., 'discriminator':...};
+        tcfg = trainer block; ocfg = optimizer._default block"""
+        self.cfg, self.tcfg, self.use_dropout = cfg, tcfg, use_dropout
+        self.sd_ae = {k: v.detach().clone() for k, v in sd_ae.items()}
+        self.sd_d = {k: v.detach().clone() for k, v in sd_d.items()}
+        buffers = ("embed", "embed_avg", "cluster_size")
+        self.p_ae = [k for k, v in self.sd_ae.items() if v.is_floating_point() and k.split(".")[-1] not in buffers
+                     and not k.endswith("position.weight")]
+        self.p_d = [k for k, v in self.sd_d.items() if v.is_floating_point()]
+        for k in self.p_ae:
+            self.sd_ae[k].requires_grad_(True)
+        for k in self.p_d:
+            self.sd_d[k].requires_grad_(True)
+        kw = dict(lr=ocfg["learning_rate"], betas=tuple(ocfg["betas"]), eps=ocfg["eps"],
+                  weight_decay=ocfg["weight_decay"])
+        self.opt_ae = torch.optim.AdamW([self.sd_ae[k] for k in self.p_ae], **kw)
+        self.opt_d = torch.optim.AdamW([self.sd_d[k] for k in self.p_d], **kw)
+
+    def step(self, mel, mel_length, wav, windows):
+        t = self.tcfg
+        losses, g_loss, predict, target, _ = O.generator_losses(
+            self.sd_ae, self.sd_d, self.cfg, mel, mel_length, wav, windows,
+            dict(t, frameshift=300, sample_rate=24000), training=True, use_dropout=self.use_dropout)
+        self.opt_d.zero_grad(set_to_none=True)
+        losses["d_loss"].backward()
+        self.opt_d.step()
+        adv = O.generator_adv_losses(self.sd_d, self.cfg, predict, target, g_loss, t.get("lambda_fm", 2))
+        losses.update(adv)
+        self.opt_ae.zero_grad(set_to_none=True)
+        for k in self.p_d:
+            self.sd_d[k].grad = None
+        adv["g_loss"].backward()
+        torch.nn.utils.clip_grad_norm_([self.sd_ae[k] for k in self.p_ae], t.get("grad_clip_thresh", 1.0))
+        self.opt_ae.step()
+        return {k: float(v) for k, v in losses.items() if torch.is_tensor(v)}
