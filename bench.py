@@ -139,8 +139,28 @@ def init_state_dicts(cfg, seed):
     return ae.state_dict(), d.state_dict()
 
 
+def pick_cpu_threads(cfg):
+    """The oracle port is thousands of small torch ops: on a many-core host all-cores oversubscribes badly
+    (measured: 128 threads were ~60x slower than 8).  Calibrate on an autoencoder forward and keep the best."""
+    from oracle import ref_modules as O
+    ncpu = os.cpu_count() or 1
+    sd_ae, _ = init_state_dicts(cfg, 1234)
+    batch = synth_batch(2, 7)
+    best, best_t = 1, float("inf")
+    for n in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
+        torch.set_num_threads(n)
+        with torch.no_grad():
+            O.msmcvqgan_forward(sd_ae, cfg["autoencoder"], batch["mel"], batch["mel_length"], False, [(100, 140)] * 2)
+            t0 = time.perf_counter()
+            O.msmcvqgan_forward(sd_ae, cfg["autoencoder"], batch["mel"], batch["mel_length"], False, [(100, 140)] * 2)
+            dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    return best, ncpu
+
+
 def time_cpu_steps(cfg, steps, warmup, B):
-    threads = os.cpu_count() or 1
+    threads, ncpu = pick_cpu_threads(cfg)
     torch.set_num_threads(threads)
     tr = build_cpu_trainer(cfg)
     batch = synth_batch(B, 99)
@@ -151,7 +171,7 @@ def time_cpu_steps(cfg, steps, warmup, B):
     for _ in range(steps):
         tr.step(batch["mel"], batch["mel_length"], batch["wav"], win)
     dt = (time.perf_counter() - t0) / max(1, steps)
-    return B * T_FRAMES / dt, dt, threads
+    return B * T_FRAMES / dt, dt, "%d (best of a sweep up to the host's %d)" % (threads, ncpu)
 
 
 def run_reference(args, rank):
@@ -319,6 +339,20 @@ def run_b200(args, rank, world, local_rank):
             if meta:
                 f["flops"] += meta["flops"]
                 f["bytes"] += meta["bytes"]
+        if os.environ.get("MSMC_BENCH_DUMP"):
+            shapes = {}
+            for name, meta, e0, e1 in prof:
+                key = name + " | " + (meta["shape"] if meta else "-")
+                d = shapes.setdefault(key, {"ms": 0.0, "calls": 0, "gflop": 0.0})
+                d["ms"] += e0.elapsed_time(e1) / 2
+                d["calls"] += 0.5
+                d["gflop"] += (meta["flops"] / 2e9) if meta else 0.0
+            rows = sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", os.environ["MSMC_BENCH_DUMP"]), "w") as f:
+                for k, d in rows:
+                    f.write("%9.3f ms  %5.1f calls  %9.2f GFLOP  %7.2f TF/s  %s\n" % (
+                        d["ms"], d["calls"], d["gflop"], d["gflop"] / max(d["ms"], 1e-9), k))
         tot_ms = sum(f["ms"] for f in fam.values())
         families = {k: {"ms_per_step": round(v["ms"] / 2, 3), "calls_per_step": v["calls"] // 2,
                         "share": round(v["ms"] / tot_ms, 3)} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}

@@ -72,6 +72,20 @@ int msmc_conv_forward(const msmc_conv_geom* g, const float* src, const float* sr
                       const float* w, const float* bias, const float* residual,
                       const float* dst_aux, float* dst, void* stream);
 
+/* Tensor-core path of msmc_conv_forward (forward form only, Cs % 32 == 0): tcgen05.mma kind::tf32 with the
+ * accumulator in TMEM; `split` != 0 selects 3xTF32 (fp32-accurate), 0 plain TF32.  The weights come as swizzled
+ * shared-memory tile images built by msmc_weight_image from the GEMM layout [T][Cs][Cd]:
+ *   role 0: forward operand;  role 1: data-gradient operand of a stride-1 conv (taps reversed, channels swapped),
+ * so the data gradient is again an msmc_conv_forward_umma call with padding d*(K-1)-p.
+ * msmc_umma_tile_n(Cd) is the N tile the kernel and the image agree on. */
+int msmc_umma_tile_n(int32_t out_channels);
+int64_t msmc_weight_image_elems(int32_t T, int32_t Cs, int32_t Cd, int32_t role, int32_t split);
+int msmc_weight_image(const float* w_gemm, float* image, int32_t T, int32_t Cs, int32_t Cd, int32_t role,
+                      int32_t split, void* stream);
+int msmc_conv_forward_umma(const msmc_conv_geom* g, const float* src, const float* src_aux, const float* wimg,
+                           const float* bias, const float* residual, const float* dst_aux, float* dst,
+                           int32_t split, void* stream);
+
 /* weight gradient of the forward form: dW[kh,kw,cs,cd] = sum_rows src_xf(src)[gathered] * gout_xf(gout)
  * (gout_xf is given in g->dst_xf with aux = dst_aux).  `workspace` holds split partial sums;
  * query its size with msmc_conv_wgrad_workspace().  dbias (optional) receives column sums of gout. */

@@ -16,9 +16,8 @@ OUT_DIR = os.path.join(HERE, "msmctts", "_b200")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(OUT_DIR, "libmsmc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math=false"] if False else \
-        ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+STAMP = os.path.join(OUT_DIR, "libmsmc_b200.stamp")
 
 
 def _digest(path, extra):
@@ -36,6 +35,11 @@ def build(verbose=True):
     headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     headers.append(os.path.join(HERE, "..", "include", "msmc_b200.h"))
     sources = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    # the library travels to the GPU box without the object cache: a stamp of all source digests lets build()
+    # recognise an up-to-date .so instead of recompiling everything there
+    stamp = " ".join(_digest(os.path.join(CSRC, src), headers) for src in sources)
+    if os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read() == stamp:
+        return LIB
     objs, rebuilt = [], False
     for src in sources:
         path = os.path.join(CSRC, src)
@@ -52,6 +56,8 @@ def build(verbose=True):
         if verbose:
             print("[build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+    with open(STAMP, "w") as f:
+        f.write(stamp)
     return LIB
 
 

@@ -2,11 +2,19 @@
 sm_100a kernel in csrc/).  Activations are channels-last: (B, H, W, C) with H == 1 for sequences.
 """
 import ctypes as C
+import os
 from collections import namedtuple
 
 import torch
 
 from . import lib as L
+
+# Contraction math of the conv / linear kernels:
+#   "3xtf32" (default) tcgen05 tensor cores, fp32 operands split hi/lo -> fp32-accurate results
+#   "tf32"             tcgen05 tensor cores, plain TF32 (the reference's cuDNN default on Ampere+)
+#   "fp32"             CUDA-core FMA kernels only
+CONV_MATH = os.environ.get("MSMC_CONV_MATH", "3xtf32")
+UMMA_MIN_ROWS = 256
 
 ConvCfg = namedtuple("ConvCfg", "KH KW sh sw dh dw ph pw reflect transposed wstr Cd pre_slope post out_hw")
 # wstr = element strides of the weight tensor for (kh, kw, cs, cd), cs = channels of the op's INPUT
@@ -41,8 +49,39 @@ def conv_out_size(n, k, s, d, p, transposed):
     return (n + 2 * p - d * (k - 1) - 1) // s + 1
 
 
+def _weight_image(w, T, Cs, Cd, role, split):
+    """swizzled tcgen05 operand image of a GEMM-layout weight [T][Cs][Cd]; cached on the tensor for its lifetime"""
+    cache = getattr(w, "_msmc_img", None)
+    if cache is None:
+        cache = {}
+        w._msmc_img = cache
+    key = (role, split)
+    img = cache.get(key)
+    if img is None:
+        n = L.load().msmc_weight_image_elems(T, Cs, Cd, role, split)
+        img = torch.empty(n, dtype=torch.float32, device=w.device)
+        L.call("msmc_weight_image", L.ptr(w), L.ptr(img), T, Cs, Cd, role, split)
+        cache[key] = img
+    return img
+
+
+def _umma_ok(src, ld_src, w, wstr_gemm, KH, KW, Cs, Cd_gemm, rows, saux, ld_saux):
+    if CONV_MATH == "fp32" or Cs % 32 != 0 or rows < UMMA_MIN_ROWS:
+        return False
+    if not w.is_contiguous() or w.numel() != KH * KW * wstr_gemm[0] * wstr_gemm[1]:
+        return False
+    if ld_src % 4 != 0 or src.data_ptr() % 16 != 0:
+        return False
+    if saux is not None and (ld_saux % 4 != 0 or saux.data_ptr() % 16 != 0):
+        return False
+    return True
+
+
 def _launch_conv(src, w, wstr, bias, residual, dst, KH, KW, sh, sw, dh, dw, ph, pw, reflect, transposed,
-                 src_xf=(L.XF_NONE, 0.0, None), dst_xf=(L.XF_NONE, 0.0, None)):
+                 src_xf=(L.XF_NONE, 0.0, None), dst_xf=(L.XF_NONE, 0.0, None), w_role=0, w_dims=None):
+    """w_role/w_dims: when the caller runs a stride-1 data gradient as a forward-form conv (taps reversed, channels
+    swapped) it passes the ORIGINAL GEMM-layout weight with w_role=1 and w_dims=(Cs_op, Cd_op); only the
+    tensor-core path can consume that, so the caller must have checked eligibility."""
     src, ld_src = _rows(src)
     B, Hs, Ws, Cs = src.shape
     _, Hd, Wd, Cd = dst.shape
@@ -70,6 +109,15 @@ def _launch_conv(src, w, wstr, bias, residual, dst, KH, KW, sh, sw, dh, dw, ph, 
         meta = {"flops": 2.0 * pos * KH * KW * Cs * Cd,
                 "bytes": 4.0 * (src.numel() + dst.numel() + KH * KW * Cs * Cd + (res.numel() if res is not None else 0)),
                 "shape": "B%d %dx%d C%d->%d k%dx%d s%d%s" % (B, Hs, Ws, Cs, Cd, KH, KW, sw, "T" if transposed else "")}
+    gemm_contig = (not transposed) and tuple(wstr) == (KW * Cs * Cd, Cs * Cd, Cd, 1)
+    if w_role == 1 or (gemm_contig and _umma_ok(src, ld_src, w, (Cs, Cd), KH, KW, Cs, Cd, B * Hd * Wd, saux,
+                                                  g.ld_saux)):
+        split = 0 if CONV_MATH == "tf32" else 1
+        cs_op, cd_op = w_dims if w_role == 1 else (Cs, Cd)
+        img = _weight_image(w, KH * KW, cs_op, cd_op, w_role, split)
+        L.call("msmc_conv_forward_umma", C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(img), L.ptr(bias), L.ptr(res),
+               L.ptr(daux), L.ptr(dst), split, meta=meta)
+        return dst
     L.call("msmc_conv_forward", C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(w), L.ptr(bias), L.ptr(res),
            L.ptr(daux), L.ptr(dst), meta=meta)
     return dst
@@ -161,8 +209,22 @@ class _ConvFn(torch.autograd.Function):
                     gx = torch.where(x > 0, gx, gx * cfg.pre_slope)
             else:
                 gx = torch.empty_like(x)
-                _launch_conv(gy, w, (s_kh, s_kw, s_cd, s_cs), None, None, gx, cfg.KH, cfg.KW, cfg.sh, cfg.sw,
-                             cfg.dh, cfg.dw, cfg.ph, cfg.pw, False, not cfg.transposed, src_xf=gmod, dst_xf=dmod)
+                Cs_op = x.shape[-1]
+                gy_r, ld_gy = _rows(gy)
+                aux_r, ld_aux = _rows(gmod[2]) if gmod[2] is not None else (None, 0)
+                if (not cfg.transposed and cfg.sh == 1 and cfg.sw == 1
+                        and cfg.wstr == (cfg.KW * Cs_op * cfg.Cd, Cs_op * cfg.Cd, cfg.Cd, 1)
+                        and _umma_ok(gy_r, ld_gy, w, (Cs_op, cfg.Cd), cfg.KH, cfg.KW, cfg.Cd, Cs_op,
+                                     gx.shape[0] * gx.shape[1] * gx.shape[2], aux_r, ld_aux)):
+                    # stride-1 data gradient == forward-form conv with reversed taps: tensor-core path
+                    _launch_conv(gy, w, (cfg.KW * cfg.Cd * Cs_op, cfg.Cd * Cs_op, Cs_op, 1), None, None, gx, cfg.KH,
+                                 cfg.KW, 1, 1, cfg.dh, cfg.dw, cfg.dh * (cfg.KH - 1) - cfg.ph,
+                                 cfg.dw * (cfg.KW - 1) - cfg.pw, False, False, src_xf=gmod, dst_xf=dmod, w_role=1,
+                                 w_dims=(Cs_op, cfg.Cd))
+                else:
+                    _launch_conv(gy, w, (s_kh, s_kw, s_cd, s_cs), None, None, gx, cfg.KH, cfg.KW, cfg.sh, cfg.sw,
+                                 cfg.dh, cfg.dw, cfg.ph, cfg.pw, False, not cfg.transposed, src_xf=gmod,
+                                 dst_xf=dmod)
         if ctx.needs_input_grad[1]:
             gw = torch.empty_like(w) if w.is_contiguous() else torch.zeros_like(w)
             want_b = ctx.has_bias and ctx.needs_input_grad[2]
@@ -220,8 +282,13 @@ def linear_cl(x, weight, bias=None, residual=None, post="none", pre_slope=None):
     lead = x.shape[:-1]
     x4 = x.reshape(-1, 1, 1, Ci)
     r4 = residual.reshape(-1, 1, 1, Co) if residual is not None else None
-    w2 = weight.reshape(Co, Ci)
-    y = conv_cl(x4, w2, bias, r4, wstr=(0, 0, 1, Ci), out_channels=Co, post=post, pre_slope=pre_slope)
+    if CONV_MATH != "fp32" and Ci % 32 == 0 and x4.shape[0] >= UMMA_MIN_ROWS and weight.requires_grad:
+        # tensor-core path wants the GEMM layout [1][Ci][Co]; the re-layout is one tiny launch
+        w_g = prep_conv_weight(weight.reshape(Co, Ci, 1))
+        y = conv_cl(x4, w_g, bias, r4, post=post, pre_slope=pre_slope)
+    else:
+        y = conv_cl(x4, weight.reshape(Co, Ci), bias, r4, wstr=(0, 0, 1, Ci), out_channels=Co, post=post,
+                    pre_slope=pre_slope)
     return y.reshape(*lead, Co)
 
 

@@ -41,6 +41,10 @@ SIGNATURES = {
     "msmc_conv_forward": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _P]),
     "msmc_conv_wgrad_workspace": (C.c_int64, [_G]),
     "msmc_conv_wgrad": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
+    "msmc_umma_tile_n": (C.c_int, [_I32]),
+    "msmc_weight_image_elems": (C.c_int64, [_I32, _I32, _I32, _I32, _I32]),
+    "msmc_weight_image": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    "msmc_conv_forward_umma": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _I32, _P]),
     "msmc_weight_norm_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I64, _I64, _I64, _P]),
     "msmc_weight_norm_bwd": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
     "msmc_reflect_pad_fold": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),

@@ -1,0 +1,117 @@
+"""tcgen05 (TF32 tensor-core) convolution path vs a plain PyTorch fp32 CPU reference.
+3xTF32 (default): same tolerance as the CUDA-core fp32 kernels (2e-5 of the tensor's max);
+plain TF32: 3e-3 (10-bit mantissa operands, fp32 accumulate)."""
+import zlib
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def close(a, b, tol, msg=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (msg, a.shape, b.shape)
+    scale = float(b.abs().max()) + 1e-12
+    err = float((a - b).abs().max())
+    assert err <= tol * scale + 1e-7, "%s max|diff| %.3e, scale %.3e (tol %.1e)" % (msg, err, scale, tol)
+
+
+CASES = [
+    # name, B, H, W, Ci, Co, KH, KW, stride, dil, pad, reflect, pre_slope, post, residual
+    ("1x1 Cs32 Cd32", 2, 1, 300, 32, 32, 1, 1, (1, 1), (1, 1), (0, 0), False, None, "none", False),
+    ("k3 Cs64 Cd64 M=517", 1, 1, 517, 64, 64, 1, 3, (1, 1), (1, 1), (0, 1), False, None, "relu", False),
+    ("mrf k11 d5 Cs64", 2, 1, 400, 64, 64, 1, 11, (1, 1), (1, 5), (0, 25), False, 0.1, "none", True),
+    ("mrf k7 d3 Cs32 Cd32", 3, 1, 1000, 32, 32, 1, 7, (1, 1), (1, 3), (0, 9), False, 0.1, "none", True),
+    ("conv_post Cd1", 2, 1, 900, 32, 1, 1, 7, (1, 1), (1, 1), (0, 3), False, 0.01, "tanh", False),
+    ("Cd100 ragged N", 2, 1, 260, 96, 100, 1, 3, (1, 1), (1, 1), (0, 1), False, None, "none", False),
+    ("Cd200 two N tiles", 2, 1, 300, 64, 200, 1, 3, (1, 1), (1, 1), (0, 1), False, None, "tanh", False),
+    ("ffn-like Cs256 Cd512", 2, 1, 240, 256, 512, 1, 3, (1, 1), (1, 1), (0, 1), False, None, "relu", False),
+    ("mpd (5,1) s(3,1) Cs64", 2, 90, 5, 64, 128, 5, 1, (3, 1), (1, 1), (2, 0), False, 0.2, "none", False),
+    ("mrd 3x3 reflect s2 Cs32", 2, 40, 30, 32, 64, 3, 3, (2, 2), (1, 1), (1, 1), True, None, "lrelu", False),
+    ("mrd 3x3 reflect s1 Cs64", 2, 21, 18, 64, 32, 3, 3, (1, 1), (1, 1), (1, 1), True, None, "lrelu", False),
+]
+
+
+def _run_case(case, tol):
+    from msmctts._b200 import functional as Fn
+    (name, B, H, W, Ci, Co, KH, KW, stride, dil, pad, reflect, pre_slope, post, use_res) = case
+    gen = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+    x = torch.randn(B, H, W, Ci, generator=gen)
+    v = torch.randn(Co, Ci, KH, KW, generator=gen) * (1.0 / (Ci * KH * KW) ** 0.5)
+    g = torch.rand(Co, 1, 1, 1, generator=gen) + 0.5
+    bias = torch.randn(Co, generator=gen) * 0.1
+    Ho = Fn.conv_out_size(H, KH, stride[0], dil[0], pad[0], False)
+    Wo = Fn.conv_out_size(W, KW, stride[1], dil[1], pad[1], False)
+    res = torch.randn(B, Ho, Wo, Co, generator=gen)
+    wgt = torch.randn(B, Ho, Wo, Co, generator=gen)
+    pslope = 0.2 if post == "lrelu" else 0.0
+    xr, vr, gr, br, rr = (t.clone().requires_grad_(True) for t in (x, v, g, bias, res))
+    w_ref = vr * (gr / vr.norm(2, dim=(1, 2, 3), keepdim=True))
+    xin = xr.permute(0, 3, 1, 2)
+    if pre_slope is not None:
+        xin = F.leaky_relu(xin, pre_slope)
+    p = pad
+    if reflect:
+        xin = F.pad(xin, (pad[1], pad[1], pad[0], pad[0]), mode="reflect")
+        p = (0, 0)
+    y_ref = F.conv2d(xin, w_ref, br, stride=stride, padding=p, dilation=dil)
+    y_ref = {"relu": F.relu, "tanh": torch.tanh, "lrelu": lambda t: F.leaky_relu(t, pslope),
+             "none": lambda t: t}[post](y_ref).permute(0, 2, 3, 1)
+    if use_res:
+        y_ref = y_ref + rr
+    (y_ref * wgt).sum().backward()
+    xc, vc, gc, bc, rc = (t.to(DEV).requires_grad_(True) for t in (x, v, g, bias, res))
+    w = Fn.prep_conv_weight(vc, gc)
+    from msmctts._b200 import lib as L
+    L.profile_begin()
+    y = Fn.conv_cl(xc, w, bc, rc if use_res else None, kernel=(KH, KW), stride=stride, dilation=dil, padding=pad,
+                   reflect=reflect, pre_slope=pre_slope, post=(post, pslope))
+    (y * wgt.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    names = [n for n, _, _, _ in L.profile_end()]
+    assert "msmc_conv_forward_umma" in names, "the tensor-core kernel did not run: %s" % names
+    close(y, y_ref, tol, "y")
+    close(xc.grad, xr.grad, tol, "dx")
+    close(vc.grad, vr.grad, max(tol, 1e-4), "dv")
+    close(bc.grad, br.grad, max(tol, 1e-4), "dbias")
+    return names
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_umma_3xtf32(case, monkeypatch):
+    from msmctts._b200 import functional as Fn
+    monkeypatch.setattr(Fn, "CONV_MATH", "3xtf32")
+    names = _run_case(case, 2e-5)
+    stride = case[8]
+    if stride == (1, 1) and not case[11] and case[5] % 32 == 0:
+        assert names.count("msmc_conv_forward_umma") == 2, "forward and stride-1 data gradient both on tensor cores"
+
+
+@pytest.mark.parametrize("case", [CASES[2], CASES[7], CASES[9]], ids=[CASES[2][0], CASES[7][0], CASES[9][0]])
+def test_conv_umma_plain_tf32(case, monkeypatch):
+    from msmctts._b200 import functional as Fn
+    monkeypatch.setattr(Fn, "CONV_MATH", "tf32")
+    _run_case(case, 3e-3)
+
+
+def test_linear_umma(monkeypatch):
+    from msmctts._b200 import functional as Fn
+    monkeypatch.setattr(Fn, "CONV_MATH", "3xtf32")
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(16, 60, 256, generator=gen)
+    W = torch.randn(384, 256, generator=gen) / 16
+    b = torch.randn(384, generator=gen)
+    xr, Wr, br = (t.clone().requires_grad_(True) for t in (x, W, b))
+    y_ref = F.linear(xr, Wr, br)
+    wgt = torch.randn(y_ref.shape, generator=gen)
+    (y_ref * wgt).sum().backward()
+    xc, Wc, bc = (t.to(DEV).requires_grad_(True) for t in (x, W, b))
+    y = Fn.linear_cl(xc, Wc, bc)
+    (y * wgt.to(DEV)).sum().backward()
+    close(y, y_ref, 2e-5, "y")
+    close(xc.grad, xr.grad, 2e-5, "dx")
+    close(Wc.grad, Wr.grad, 1e-4, "dW")
+    close(bc.grad, br.grad, 1e-4, "db")
