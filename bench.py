@@ -171,7 +171,7 @@ def time_cpu_steps(cfg, steps, warmup, B):
     for _ in range(steps):
         tr.step(batch["mel"], batch["mel_length"], batch["wav"], win)
     dt = (time.perf_counter() - t0) / max(1, steps)
-    return B * T_FRAMES / dt, dt, "%d (best of a sweep up to the host's %d)" % (threads, ncpu)
+    return B * T_FRAMES / dt, dt, threads, ncpu
 
 
 def run_reference(args, rank):
@@ -180,9 +180,10 @@ def run_reference(args, rank):
         return
     # bounded: each step is a B=4 sample of the B=16 workload; cap the step count so the run stays within minutes
     steps, warmup = min(args.steps, 12), min(args.warmup, 2)
-    value, dt, threads = time_cpu_steps(cfg, steps, warmup, CPU_SAMPLE_B)
-    sample = "full GAN train step on a B=%d slice of the B=%d batch, T=%d, %d timed steps after %d warm-up" % (
-        CPU_SAMPLE_B, B_PER_GPU, T_FRAMES, steps, warmup)
+    value, dt, threads, ncpu = time_cpu_steps(cfg, steps, warmup, CPU_SAMPLE_B)
+    sample = ("full GAN train step on a B=%d slice of the B=%d batch, T=%d, %d timed steps after %d warm-up; %d torch "
+              "threads = fastest of a sweep up to the host's %d logical CPUs") % (
+        CPU_SAMPLE_B, B_PER_GPU, T_FRAMES, steps, warmup, threads, ncpu)
     print(json.dumps({
         "impl": "reference", "metric": "mel-frames/sec MSMC-VQ-GAN train step", "value": value,
         "unit": "mel-frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3,
@@ -202,7 +203,7 @@ def workload_config(n):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def build_gpu_trainer(cfg, device, distributed, rank, world):
+def build_gpu_trainer(cfg, device, distributed, rank, world, use_graph=False):
     from msmctts.tasks.msmc_tts import MSMCTTS
     from msmctts.trainers.msmctts_trainer import VQGANTrainer
     from msmctts.utils.config import Config
@@ -219,6 +220,7 @@ def build_gpu_trainer(cfg, device, distributed, rank, world):
     kwargs = config.trainer.to_dict()
     kwargs.pop("_name")
     kwargs["warmup_steps"] = 0      # bench the post-warm-up (GAN) step
+    kwargs["cuda_graph"] = use_graph
     trainer = VQGANTrainer(config, task, num_gpus=world, rank=rank, **kwargs)
     trainer.build_optimizer()
     task.train()
@@ -274,7 +276,7 @@ def run_b200(args, rank, world, local_rank):
     if distributed and not dist.is_initialized():
         dist.init_process_group("nccl")
     cfg = load_cfg()
-    trainer = build_gpu_trainer(cfg, device, distributed, rank, world)
+    trainer = build_gpu_trainer(cfg, device, distributed, rank, world, use_graph=not args.no_graph)
     pk = peaks()
     fixed_win = [(100, 100 + WIN_FRAMES)] * B_PER_GPU
     dev_batch = synth_batch(B_PER_GPU, 1000 + rank, device=device)
@@ -308,12 +310,13 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
-    for i in range(max(3, args.warmup)):
-        step_resident(i)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = L.launch_count
+    step_resident(0)                  # first call is always eager: count the kernels one step launches
+    launches = L.launch_count - l0
+    for i in range(max(3, args.warmup) + 3):     # +3: eager warm-ups before the graph is captured
+        step_resident(1 + i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_step = timed(step_resident, args.steps)
-    launches = (L.launch_count - l0) // args.steps
     clocks = sampler.stop() if sampler else None
     for i in range(2):
         step_e2e(i)
@@ -325,7 +328,8 @@ def run_b200(args, rank, world, local_rank):
 
     roof, families, vq = None, None, None
     if rank == 0:
-        # ---- roofline pass: CUDA events around every C-ABI call of two more steps (same stream)
+        # ---- roofline pass: CUDA events around every C-ABI call of two more EAGER steps (same stream)
+        trainer.use_cuda_graph = False
         L.profile_begin()
         for i in range(2):
             step_resident(100 + i)
@@ -374,10 +378,11 @@ def run_b200(args, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, threads = time_cpu_steps(cfg, 2, 1, CPU_SAMPLE_B)
+        v, dt, threads, ncpu = time_cpu_steps(cfg, 2, 1, CPU_SAMPLE_B)
         cpu = {"value": v, "unit": "mel-frames/s", "cores": threads, "kind": "port",
                "sample": "oracle port of the same full GAN step on a B=%d slice of the batch, 2 timed steps after 1 "
-                         "warm-up (%.1f s/step)" % (CPU_SAMPLE_B, dt)}
+                         "warm-up (%.1f s/step); %d torch threads = fastest of a sweep up to the host's %d logical "
+                         "CPUs" % (CPU_SAMPLE_B, dt, threads, ncpu)}
     if rank == 0:
         print(json.dumps({
             "metric": "mel-frames/sec MSMC-VQ-GAN train step", "value": value, "unit": "mel-frames/s",
@@ -387,6 +392,7 @@ def run_b200(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "mel-frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+            "cuda_graph": not args.no_graph,
             "roofline": roof, "kernel_families": families, "vq_argmin": vq, "cpu_baseline": cpu}))
     if distributed:
         dist.barrier()
@@ -400,6 +406,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

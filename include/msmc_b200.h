@@ -77,14 +77,22 @@ int msmc_conv_forward(const msmc_conv_geom* g, const float* src, const float* sr
  * shared-memory tile images built by msmc_weight_image from the GEMM layout [T][Cs][Cd]:
  *   role 0: forward operand;  role 1: data-gradient operand of a stride-1 conv (taps reversed, channels swapped),
  * so the data gradient is again an msmc_conv_forward_umma call with padding d*(K-1)-p.
- * msmc_umma_tile_n(Cd) is the N tile the kernel and the image agree on. */
-int msmc_umma_tile_n(int32_t out_channels);
-int64_t msmc_weight_image_elems(int32_t T, int32_t Cs, int32_t Cd, int32_t role, int32_t split);
+ * msmc_umma_tile_n(Cd, rows) proposes the N tile (32/64/128) that fills the SMs; image and kernel must be given
+ * the same BN. */
+int msmc_umma_tile_n(int32_t out_channels, int64_t rows);
+int64_t msmc_weight_image_elems(int32_t T, int32_t Cs, int32_t Cd, int32_t role, int32_t split, int32_t BN);
 int msmc_weight_image(const float* w_gemm, float* image, int32_t T, int32_t Cs, int32_t Cd, int32_t role,
-                      int32_t split, void* stream);
+                      int32_t split, int32_t BN, void* stream);
 int msmc_conv_forward_umma(const msmc_conv_geom* g, const float* src, const float* src_aux, const float* wimg,
                            const float* bias, const float* residual, const float* dst_aux, float* dst,
-                           int32_t split, void* stream);
+                           int32_t split, int32_t BN, void* stream);
+
+/* tensor-core weight gradient (Cs % 32 == 0): both operands are consumed MN-major straight from the channels-last
+ * activations; same contract and workspace layout as msmc_conv_wgrad */
+int64_t msmc_conv_wgrad_umma_workspace(const msmc_conv_geom* g);
+int msmc_conv_wgrad_umma(const msmc_conv_geom* g, const float* src, const float* src_aux, const float* gout,
+                         const float* gout_aux, float* dw, float* dbias, float* workspace, int64_t workspace_bytes,
+                         int32_t split, void* stream);
 
 /* weight gradient of the forward form: dW[kh,kw,cs,cd] = sum_rows src_xf(src)[gathered] * gout_xf(gout)
  * (gout_xf is given in g->dst_xf with aux = dst_aux).  `workspace` holds split partial sums;
@@ -161,13 +169,13 @@ int msmc_add_layernorm_bwd(const float* gy, const float* xhat, const float* rstd
  * Spectral front end of the multi-resolution discriminator and MelLoss (a13, a17;
  * utils/audio.py:398-419,348-376, criterions/stft_loss.py:78-107).  The windowed DFT itself is a
  * msmc_conv_forward with Cs = 1; these are the HBM-bound point-wise stages around it.
- *   spec : (rows, 2*F) = [re(0..F) | im(0..F)] ;  mag = sqrt(max(re^2+im^2, floor_)) (floor_add=0)
- *                                                 or  sqrt(re^2+im^2+floor_)          (floor_add=1)
+ *   spec : (rows, 2*Fp) = [re(0..F) pad | im(0..F) pad], Fp >= F (channel padding keeps the spectrum GEMMs on the
+ *   tensor-core path); mag (rows, F) = sqrt(max(re^2+im^2, floor_)) (floor_add=0) or sqrt(re^2+im^2+floor_) (=1)
  * ------------------------------------------------------------------------------------------- */
-int msmc_spec_magnitude_fwd(const float* spec, float* mag, int64_t rows, int32_t F, float floor_,
+int msmc_spec_magnitude_fwd(const float* spec, float* mag, int64_t rows, int32_t F, int32_t Fp, float floor_,
                             int32_t floor_add, void* stream);
 int msmc_spec_magnitude_bwd(const float* gmag, const float* spec, const float* mag, float* gspec,
-                            int64_t rows, int32_t F, float floor_, int32_t floor_add, void* stream);
+                            int64_t rows, int32_t F, int32_t Fp, float floor_, int32_t floor_add, void* stream);
 /* 'double' domain (audio.py:414-417): out[...,0] = mel, out[...,1] = clamp((20 log10(mel) - ref + 100)/100, 0, 1)
  * mel : (rows, F) -> out : (rows, F, 2) channels-last */
 int msmc_mel_double_fwd(const float* mel, float* out, int64_t n, float ref_db, float min_db, void* stream);
@@ -176,6 +184,11 @@ int msmc_mel_double_bwd(const float* gout, const float* mel, float* gmel, int64_
 /* log-compression of MelLoss: out = log(max(x, clip)) and its backward */
 int msmc_log_clamp_fwd(const float* x, float* y, int64_t n, float clip, void* stream);
 int msmc_log_clamp_bwd(const float* gy, const float* x, float* gx, int64_t n, float clip, void* stream);
+
+/* backward of reflect-padded STFT framing (torch.stft center/reflect, audio.py:399; stft_loss.py:88-99): overlap-add
+ * the per-frame time-domain gradients gframes (B, frames, win) onto x (B, L) and fold the reflected borders */
+int msmc_overlap_add_fold(const float* gframes, float* gx, int32_t B, int32_t frames, int32_t win, int32_t hop,
+                          int32_t L, int32_t pad, void* stream);
 
 /* gated activation of the WaveNet-style ResStack (modules.py:172-179): out = tanh(x[:, :C]) * sigmoid(x[:, C:]) */
 int msmc_gated_act_fwd(const float* x, float* y, int64_t rows, int32_t C, void* stream);

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "msmctts", "_b200")
-OBJ_DIR = os.path.join(HERE, "build")
+OBJ_DIR = os.environ.get("MSMC_OBJ_DIR", "/tmp/msmc_b200_obj")   # object cache lives outside the tree
 LIB = os.path.join(OUT_DIR, "libmsmc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]

@@ -61,5 +61,8 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 int num_sms();
+// second pass of every weight-gradient kernel: sum the per-slice partials, scatter through the weight strides
+int launch_wgrad_reduce(const msmc_conv_geom& g, const float* workspace, int splits, float* dw, float* dbias,
+                        void* stream);
 
 }  // namespace msmc

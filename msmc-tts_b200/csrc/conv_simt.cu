@@ -590,6 +590,18 @@ int pick_bn(int cd) { return cd <= 16 ? 16 : (cd <= 32 ? 32 : (cd <= 64 ? 64 : 1
 }  // namespace
 }  // namespace msmc
 
+namespace msmc {
+int launch_wgrad_reduce(const msmc_conv_geom& g, const float* workspace, int splits, float* dw, float* dbias,
+                        void* stream) {
+  const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
+  const int64_t total = Ktot * g.Cd + g.Cd;
+  int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 8);
+  wgrad_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, workspace, splits, dw, dbias);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+}  // namespace msmc
+
 using namespace msmc;
 
 extern "C" int msmc_conv_forward(const msmc_conv_geom* gp, const float* src, const float* src_aux,
@@ -682,11 +694,7 @@ extern "C" int msmc_conv_wgrad(const msmc_conv_geom* gp, const float* src, const
     default: conv_wgrad_kernel<128><<<grid, NTHREADS, 0, st>>>(a); break;
   }
   MSMC_CHECK_LAUNCH();
-  const int64_t total = Ktot * g.Cd + g.Cd;
-  int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 8);
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(g, workspace, splits, dw, dbias);
-  MSMC_CHECK_LAUNCH();
-  return MSMC_OK;
+  return launch_wgrad_reduce(g, workspace, splits, dw, dbias, stream);
 }
 
 extern "C" int msmc_weight_norm_fwd(const float* v, const float* g, float* w, float* inv_norm, int32_t O,

@@ -122,11 +122,34 @@ __device__ __forceinline__ int reflect1(int i, int n) {
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-template <int BN, bool SPLIT, int STAGES>
-__global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const UmmaArgs a) {
+// operand-transform classes the producer is specialised on (keeps the per-element code straight-line)
+constexpr int XFC_NONE = 0, XFC_LRELU = 1, XFC_GENERIC = 2;
+
+template <int XFC>
+__device__ __forceinline__ float4 xf4(const msmc_conv_geom& g, float4 x, float4 ax) {
+  if (XFC == XFC_LRELU) {
+    // slope in (0, 1): leaky_relu(x) == max(x, slope * x)
+    const float sl = g.src_slope;
+    x.x = fmaxf(x.x, sl * x.x); x.y = fmaxf(x.y, sl * x.y); x.z = fmaxf(x.z, sl * x.z); x.w = fmaxf(x.w, sl * x.w);
+  } else if (XFC == XFC_GENERIC) {
+    x.x = apply_xf(g.src_xf, g.src_slope, x.x, ax.x);
+    x.y = apply_xf(g.src_xf, g.src_slope, x.y, ax.y);
+    x.z = apply_xf(g.src_xf, g.src_slope, x.z, ax.z);
+    x.w = apply_xf(g.src_xf, g.src_slope, x.w, ax.w);
+  }
+  return x;
+}
+
+constexpr int UMF_PRODUCERS = 256;             // 8 producer / epilogue warps
+constexpr int UMF_THREADS = UMF_PRODUCERS + 32;  // + the MMA warp
+
+constexpr int UM_MAX_PHASE_TAPS = 256;
+
+template <int BN, bool SPLIT, int STAGES, int XFC, bool TRANSPOSED>
+__global__ void __launch_bounds__(UMF_THREADS, 1) conv_umma_kernel(const UmmaArgs a) {
   const msmc_conv_geom& g = a.g;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: A stages (16 KB each), B stages (BN*128 B each), barriers, tmem slot
+  // carve: A stages (16 KB per plane), B stages (BN*128 B per plane), barriers, tmem slot
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int NP = SPLIT ? 2 : 1;             // planes per operand: hi (, lo)
   constexpr int A_PLANE = UM_BM * 128;
@@ -141,23 +164,65 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const UmmaArgs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
+  // conv-transpose form: blockIdx.z is the phase (hd % sh, wd % sw); its destination rows form a regular
+  // sub-grid and only the taps congruent with the phase contribute (no wasted taps)
+  __shared__ short s_tap_kh[UM_MAX_PHASE_TAPS];
+  __shared__ short s_tap_kw[UM_MAX_PHASE_TAPS];
+  __shared__ int s_ntaps;
+  int prh = 0, prw = 0, step_h = 1, step_w = 1;
+  if (TRANSPOSED) {
+    prh = blockIdx.z / g.sw;
+    prw = blockIdx.z % g.sw;
+    step_h = g.sh;
+    step_w = g.sw;
+  }
+  const int Hp = TRANSPOSED ? (g.Hd - prh + step_h - 1) / step_h : g.Hd;
+  const int Wp = TRANSPOSED ? (g.Wd - prw + step_w - 1) / step_w : g.Wd;
+  const int64_t M = (int64_t)g.B * Hp * Wp;
   const int64_t m0 = (int64_t)blockIdx.x * UM_BM;
+  if (m0 >= M) return;                       // (uniform per CTA; phases have slightly different row counts)
   const int n_tile = blockIdx.y;
   const int n_tiles = gridDim.y;
   const int KC = g.Cs / UM_BK;
-  const int T = g.KH * g.KW;
+  int T = g.KH * g.KW;
+  if (TRANSPOSED) {
+    if (tid == 0) {
+      auto gcd = [](int x, int y) { while (y) { int t = x % y; x = y; y = t; } return x; };
+      auto first_valid = [](int r, int p, int d, int s, int period, int K) {
+        for (int k = 0; k < period && k < K; ++k) {
+          int t = r + p - k * d;
+          if (((t % s) + s) % s == 0) return k;
+        }
+        return K;
+      };
+      const int per_h = g.sh / gcd(g.dh % g.sh == 0 ? g.sh : g.dh % g.sh, g.sh);
+      const int per_w = g.sw / gcd(g.dw % g.sw == 0 ? g.sw : g.dw % g.sw, g.sw);
+      const int kh0 = first_valid(prh, g.ph, g.dh, g.sh, per_h, g.KH);
+      const int kw0 = first_valid(prw, g.pw, g.dw, g.sw, per_w, g.KW);
+      int c = 0;
+      for (int kh = kh0; kh < g.KH; kh += per_h)
+        for (int kw = kw0; kw < g.KW && c < UM_MAX_PHASE_TAPS; kw += per_w) {
+          s_tap_kh[c] = (short)kh;
+          s_tap_kw[c] = (short)kw;
+          ++c;
+        }
+      s_ntaps = c;
+    }
+    __syncthreads();
+    T = s_ntaps;
+  }
   const int n_k = T * KC;
+  constexpr int MMA_WARP = UMF_PRODUCERS / 32;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 128 + 1);   // 128 producer arrivals + 1 arrive.expect_tx for the weight tile
-      mbar_init(&empty_bar[s], 1);        // one tcgen05.commit
+      mbar_init(&full_bar[s], UMF_PRODUCERS + 1);   // producer arrivals + 1 arrive.expect_tx for the weight tile
+      mbar_init(&empty_bar[s], 1);                  // one tcgen05.commit
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     // allocate BN TMEM columns (power of two >= 32); the address lands in shared memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)(BN < 32 ? 32 : BN))
@@ -169,95 +234,149 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const UmmaArgs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < MMA_WARP) {
     // ================================= A producers =================================
-    const int64_t m = m0 + tid;
-    const bool row_ok = m < M;
-    int b = 0, hd = 0, wd = 0;
-    if (row_ok) {
-      b = (int)(m / ((int64_t)g.Hd * g.Wd));
-      const int rem = (int)(m % ((int64_t)g.Hd * g.Wd));
-      hd = rem / g.Wd;
-      wd = rem - hd * g.Wd;
+    // Coalesced mapping: one warp instruction reads 4 output rows x 8 sixteen-byte chunks (4 full 128 B lines);
+    // thread t owns chunk (t & 7) of rows (t >> 3) + 32*i, i = 0..3.
+    const int chunk = tid & 7;
+    const int rsub = tid >> 3;                 // 0..31
+    const int r8 = rsub & 7;                   // (row & 7) is the same for all rows of this thread
+    int pixb[4], hs0[4], ws0[4];               // batch pixel base / top-left source coordinate of each row
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t m = m0 + rsub + 32 * i;
+      if (m < M) {
+        const int b = (int)(m / ((int64_t)Hp * Wp));
+        const int rem = (int)(m % ((int64_t)Hp * Wp));
+        const int hd = prh + (rem / Wp) * step_h, wd = prw + (rem % Wp) * step_w;
+        pixb[i] = b * g.Hs * g.Ws;
+        hs0[i] = TRANSPOSED ? hd + g.ph : hd * g.sh - g.ph;
+        ws0[i] = TRANSPOSED ? wd + g.pw : wd * g.sw - g.pw;
+      } else {
+        pixb[i] = -1; hs0[i] = 0; ws0[i] = 0;
+      }
     }
-    const bool need_aux = xf_needs_aux(g.src_xf);
-    const int r8 = tid & 7;
-    const uint32_t row_off = (uint32_t)(tid >> 3) * 1024u + (uint32_t)r8 * 128u;
-    float4 v[8], u[8];
+    constexpr bool NEED_AUX = (XFC == XFC_GENERIC);
+    const bool need_aux = NEED_AUX && xf_needs_aux(g.src_xf);
+    float4 v[4], u[4];
+    int kc_n = 0, kh_n = 0, kw_n = 0, ti_n = 0;   // (chunk, tap) of the NEXT stage to gather
+    if (TRANSPOSED && T > 0) { kh_n = s_tap_kh[0]; kw_n = s_tap_kw[0]; }
 
     // raw global loads only (no dependent math), so they stay in flight across the barrier round-trip
-    auto gather = [&](int ks) {
-      const int t = ks / KC, kc = ks - t * KC;
-      const int kh = t / g.KW, kw = t - kh * g.KW;
-      int hs = hd * g.sh + kh * g.dh - g.ph;
-      int ws = wd * g.sw + kw * g.dw - g.pw;
-      bool ok = row_ok;
-      if (g.pad_reflect) {
-        hs = reflect1(hs, g.Hs);
-        ws = reflect1(ws, g.Ws);
-      } else {
-        ok = ok && hs >= 0 && hs < g.Hs && ws >= 0 && ws < g.Ws;
-      }
-      if (ok) {
-        const int64_t pix = ((int64_t)b * g.Hs + hs) * g.Ws + ws;
-        const float4* p = reinterpret_cast<const float4*>(a.src + pix * g.ld_src + kc * UM_BK);
+    auto gather = [&]() {
+      const int coff = kc_n * UM_BK + chunk * 4;
+      const int dh = kh_n * g.dh, dw = kw_n * g.dw;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = __ldg(p + c);
-        if (need_aux) {
-          const float4* q = reinterpret_cast<const float4*>(a.src_aux + pix * g.ld_saux + kc * UM_BK);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) u[c] = __ldg(q + c);
+      for (int i = 0; i < 4; ++i) {
+        int hs, ws;
+        bool ok = pixb[i] >= 0;
+        if (TRANSPOSED) {
+          // the phase guarantees divisibility; only the range has to be checked
+          const int th = hs0[i] - dh, tw = ws0[i] - dw;
+          hs = th / g.sh;
+          ws = tw / g.sw;
+          ok = ok && th >= 0 && tw >= 0 && hs < g.Hs && ws < g.Ws;
+        } else {
+          hs = hs0[i] + dh;
+          ws = ws0[i] + dw;
+          if (g.pad_reflect) {
+            hs = reflect1(hs, g.Hs);
+            ws = reflect1(ws, g.Ws);
+          } else {
+            ok = ok && (unsigned)hs < (unsigned)g.Hs && (unsigned)ws < (unsigned)g.Ws;
+          }
         }
-      } else {
-        // padding: every operand transform maps 0 -> 0, so zeros pass through the store path unchanged
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { v[c] = make_float4(0.f, 0.f, 0.f, 0.f); u[c] = v[c]; }
+        if (ok) {
+          const int pix = pixb[i] + hs * g.Ws + ws;
+          v[i] = __ldg(reinterpret_cast<const float4*>(a.src + (int64_t)pix * g.ld_src + coff));
+          if (NEED_AUX && need_aux)
+            u[i] = __ldg(reinterpret_cast<const float4*>(a.src_aux + (int64_t)pix * g.ld_saux + coff));
+        } else {
+          // padding: every operand transform maps 0 -> 0, so zeros pass through the store path unchanged
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (NEED_AUX) u[i] = v[i];
+        }
+      }
+      if (++kc_n == KC) {
+        kc_n = 0;
+        if (TRANSPOSED) {
+          ++ti_n;
+          if (ti_n < T) { kh_n = s_tap_kh[ti_n]; kw_n = s_tap_kw[ti_n]; }
+        } else if (++kw_n == g.KW) { kw_n = 0; ++kh_n; }
       }
     };
 
-    gather(0);
+    gather();
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t dst_off = (uint32_t)(rsub >> 3) * 1024u + (uint32_t)r8 * 128u + (uint32_t)((chunk ^ r8) << 4);
     for (int ks = 0; ks < n_k; ++ks) {
-      const int s = ks % STAGES;
-      const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
       mbar_wait(&empty_bar[s], ph ^ 1u);
       if (tid == 0) {
         mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
-        const float* wsrc = a.wimg + ((int64_t)ks * n_tiles + n_tile) * (B_BYTES / 4);
+        int64_t wk = ks;                                   // (tap * KC + chunk) of this stage
+        if (TRANSPOSED) {
+          const int ti = ks / KC, kc = ks - ti * KC;
+          wk = (int64_t)(s_tap_kh[ti] * g.KW + s_tap_kw[ti]) * KC + kc;
+        }
+        const float* wsrc = a.wimg + (wk * n_tiles + n_tile) * (B_BYTES / 4);
         bulk_g2s(sB + s * B_BYTES, wsrc, B_BYTES, &full_bar[s]);
       }
-      uint8_t* dstrow = sA + s * A_BYTES + row_off;
+      uint8_t* dstbase = sA + s * A_BYTES + dst_off;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 x = v[c];
-        if (g.src_xf != MSMC_XF_NONE) {
-          const float4 ax = need_aux ? u[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-          x.x = apply_xf(g.src_xf, g.src_slope, x.x, ax.x);
-          x.y = apply_xf(g.src_xf, g.src_slope, x.y, ax.y);
-          x.z = apply_xf(g.src_xf, g.src_slope, x.z, ax.z);
-          x.w = apply_xf(g.src_xf, g.src_slope, x.w, ax.w);
-        }
+      for (int i = 0; i < 4; ++i) {
+        const float4 x = xf4<XFC>(g, v[i], NEED_AUX ? u[i] : make_float4(0.f, 0.f, 0.f, 0.f));
+        uint8_t* d = dstbase + i * 4096;        // rows advance by 32 -> four 1 KB swizzle atoms
         if (SPLIT) {
           const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-          *reinterpret_cast<float4*>(dstrow + ((c ^ r8) << 4)) = hi;
-          *reinterpret_cast<float4*>(dstrow + A_PLANE + ((c ^ r8) << 4)) =
-              make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+          *reinterpret_cast<float4*>(d) = hi;
+          *reinterpret_cast<float4*>(d + A_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
         } else {
-          *reinterpret_cast<float4*>(dstrow + ((c ^ r8) << 4)) = x;
+          *reinterpret_cast<float4*>(d) = x;
         }
       }
-      if (ks + 1 < n_k) gather(ks + 1);   // issue the next stage's loads before signalling this one
+      if (ks + 1 < n_k) gather();   // issue the next stage's loads before signalling this one
       fence_proxy_async();
       mbar_arrive(&full_bar[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
 
     // ================================= epilogue =================================
+    // TMEM lane == accumulator row; warps w and w+4 share lanes 32*(w%4).. and split the columns
+    const int lane_grp = warp & 3;
+    const int64_t mt = m0 + lane_grp * 32 + (tid & 31);      // row inside this phase
+    const bool row_ok = mt < M;
+    int64_t m = mt;                                          // destination pixel index
+    if (TRANSPOSED && row_ok) {
+      const int b = (int)(mt / ((int64_t)Hp * Wp));
+      const int rem = (int)(mt % ((int64_t)Hp * Wp));
+      m = ((int64_t)b * g.Hd + prh + (rem / Wp) * step_h) * g.Wd + prw + (rem % Wp) * step_w;
+    }
+    if (n_k == 0) {
+      // a phase without taps still owes bias / zeros to its destination rows
+      if (row_ok) {
+        const int n0z = n_tile * BN;
+        for (int j = (warp >> 2) * (BN / 2); j < (warp >> 2) * (BN / 2) + BN / 2; ++j) {
+          const int n = n0z + j;
+          if (n < g.Cd) {
+            float x = a.bias ? __ldg(a.bias + n) : 0.f;
+            if (g.dst_xf != MSMC_XF_NONE)
+              x = apply_xf(g.dst_xf, g.dst_slope, x, xf_needs_aux(g.dst_xf) ? __ldg(a.dst_aux + m * g.ld_daux + n) : 0.f);
+            if (a.residual) x += __ldg(a.residual + m * g.ld_res + n);
+            a.dst[m * g.ld_dst + n] = x;
+          }
+        }
+      }
+    } else {
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
     const int n0 = n_tile * BN;
     const bool dneed_aux = xf_needs_aux(g.dst_xf);
+    constexpr int CHALF = BN / 2;
+    const int cbeg = (warp >> 2) * CHALF;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+    for (int c0 = cbeg; c0 < cbeg + CHALF; c0 += 16) {
       float acc[16];
       tmem_ld16(taddr + (uint32_t)c0, acc);
       if (row_ok) {
@@ -287,16 +406,17 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const UmmaArgs
         }
       }
     }
+    }
     tc_fence_before();
   } else {
-    // ================================= MMA issuer (warp 4) =================================
+    // ================================= MMA issuer =================================
     // instruction descriptor: D = F32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)(UM_BM >> 4) << 24);
     if ((tid & 31) == 0) {
+      int s = 0;
+      uint32_t ph = 0;
       for (int ks = 0; ks < n_k; ++ks) {
-        const int s = ks % STAGES;
-        const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
@@ -315,13 +435,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const UmmaArgs
           }
         }
         umma_commit(&empty_bar[s]);   // frees the stage when these MMAs have read it
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
-      umma_commit(accum_bar);
+      if (n_k > 0) umma_commit(accum_bar);
     }
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)(BN < 32 ? 32 : BN))
@@ -329,9 +450,290 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv_umma_kernel(const UmmaArgs
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores:  dW[(tap, cs), cd] = sum_m  xf(src)[gather(m, tap), cs] * xf(gout)[m, cd]
+//
+// The reduction runs over output positions m, which are the OUTER index of both channels-last operands, so both
+// UMMA operands are MN-major: a 128-byte shared-memory row is "32 consecutive channels of one position", four
+// consecutive positions form one SWIZZLE_128B_BASE32B atom (the only MN-major layout TF32 has; one tcgen05.mma
+// with K=8 spans two atoms, SBO = 512 B), 32-channel blocks sit LBO = 4 KB apart.  One CTA owns 4 row-blocks of dW (a row-block = 32 channels of one tap -> M = 128 accumulator lanes) x BN
+// output channels and loops over its slice of positions, 32 per stage.  Producer thread (blk = warp, p = lane)
+// gathers one 128-byte row per operand per stage; lanes are positions, so the bias gradient (column sums of gout)
+// is a warp-shuffle reduction.  Partial sums per position-slice go to the workspace and are reduced by the same
+// deterministic second pass as the CUDA-core path.
+// ------------------------------------------------------------------------------------------------------------
+struct UmmaWgradArgs {
+  msmc_conv_geom g;
+  const float* src;
+  const float* src_aux;
+  const float* gout;
+  const float* gout_aux;
+  float* partial;          // [splits][Ktot*Cd + Cd]
+  int64_t rows_per_split;  // multiple of 32
+  int want_bias;
+  int gvec;                // gout rows can be read with 16-byte loads
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  // MN-major TF32 operands only exist in the SWIZZLE_128B_BASE32B layout (layout type 1, cute
+  // Layout_MN_SW128_32B_Atom: 128-byte rows of 32 MN elements, 4 K-rows per atom, 32-byte chunks XORed with
+  // row & 3).  LBO = 4096 B between 32-element MN blocks, SBO = 512 B between 4-row K groups.
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+// byte offset of 16-byte chunk `c16` of K-row `p` inside one 32-channel block of an MN-major operand tile
+__device__ __forceinline__ uint32_t mn_off(int p, int c16) {
+  return (uint32_t)p * 128u + (uint32_t)(((((c16 >> 1) ^ (p & 3)) << 1) | (c16 & 1)) << 4);
+}
+
+template <int BN, bool SPLIT, int STAGES, int XFC>
+__global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const UmmaWgradArgs a) {
+  const msmc_conv_geom& g = a.g;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NP = SPLIT ? 2 : 1;
+  constexpr int A_PLANE = 4 * 4096;            // 4 row-blocks x 32 positions x 128 B
+  constexpr int NB = BN / 32;                  // 32-channel blocks of the gout operand
+  constexpr int B_PLANE = NB * 4096;
+  constexpr int A_BYTES = NP * A_PLANE;
+  constexpr int B_BYTES = NP * B_PLANE;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KC = g.Cs / 32;
+  const int RB = g.KH * g.KW * KC;                     // row-blocks of dW
+  const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
+  const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
+  const int rb0 = blockIdx.x * 4;
+  const int n0 = blockIdx.y * BN;
+  const int64_t mbeg = (int64_t)blockIdx.z * a.rows_per_split;
+  const int64_t mend = min(M, mbeg + a.rows_per_split);
+  const int n_k = (int)((mend - mbeg + 31) / 32);      // stages of 32 positions (>= 1 by construction)
+  constexpr int MMA_WARP = UMF_PRODUCERS / 32;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], UMF_PRODUCERS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < MMA_WARP) {
+    // =============== producers: warps 0-3 stage the source operand, warps 4-7 the output-gradient operand ===============
+    // warp (mod 4) = 32-channel block; inside the warp one instruction reads 4 positions x 128 B:
+    // thread owns 16-byte chunk (lane & 7) of positions (lane >> 3) + 4*i, i = 0..7.
+    const bool is_a = warp < 4;
+    const int blk = warp & 3;
+    const int chunk = lane & 7;
+    const int psub = lane >> 3;                // 0..3
+    // A side: which (tap, channel block) this warp stages
+    const int rb = rb0 + blk;
+    const bool rb_ok = rb < RB;
+    int tap = 0, cb = 0, kh = 0, kw = 0;
+    if (rb_ok) { tap = rb / KC; cb = rb - tap * KC; kh = tap / g.KW; kw = tap - kh * g.KW; }
+    // B side
+    const bool nb_ok = blk < NB;
+    const int nbase = n0 + blk * 32;
+    const bool gvec_ok = a.gvec && (nbase + 32 <= g.Cd);
+    const bool gneed_aux = xf_needs_aux(g.dst_xf);
+    constexpr bool NEED_AUX = (XFC == XFC_GENERIC);
+    const bool need_aux = NEED_AUX && xf_needs_aux(g.src_xf);
+    const bool do_bias = a.want_bias && blockIdx.x == 0 && !is_a && nb_ok;
+    const bool active = is_a ? true : nb_ok;
+    float4 v[8], u[8];
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    int64_t m_next = mbeg + psub;              // position of row i = 0 of the next stage to gather
+
+    auto gather = [&]() {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m = m_next + 4 * i;
+        const bool m_ok = m < mend;
+        if (is_a) {
+          bool ok = m_ok && rb_ok;
+          int64_t pix = 0;
+          if (ok) {
+            const int b = (int)(m / ((int64_t)g.Hd * g.Wd));
+            const int rem = (int)(m % ((int64_t)g.Hd * g.Wd));
+            const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
+            int hs = hd * g.sh + kh * g.dh - g.ph;
+            int ws = wd * g.sw + kw * g.dw - g.pw;
+            if (g.pad_reflect) { hs = reflect1(hs, g.Hs); ws = reflect1(ws, g.Ws); }
+            else ok = (unsigned)hs < (unsigned)g.Hs && (unsigned)ws < (unsigned)g.Ws;
+            pix = ((int64_t)b * g.Hs + hs) * g.Ws + ws;
+          }
+          if (ok) {
+            v[i] = __ldg(reinterpret_cast<const float4*>(a.src + pix * g.ld_src + cb * 32 + chunk * 4));
+            if (NEED_AUX && need_aux)
+              u[i] = __ldg(reinterpret_cast<const float4*>(a.src_aux + pix * g.ld_saux + cb * 32 + chunk * 4));
+          } else {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (NEED_AUX) u[i] = v[i];
+          }
+        } else if (nb_ok) {
+          if (m_ok && gvec_ok) {
+            v[i] = __ldg(reinterpret_cast<const float4*>(a.gout + m * g.ld_dst + nbase + chunk * 4));
+            if (gneed_aux)
+              u[i] = __ldg(reinterpret_cast<const float4*>(a.gout_aux + m * g.ld_daux + nbase + chunk * 4));
+          } else {
+            float t4[4], u4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = nbase + chunk * 4 + j;
+              const bool in = m_ok && n < g.Cd;
+              t4[j] = in ? __ldg(a.gout + m * g.ld_dst + n) : 0.f;
+              u4[j] = (in && gneed_aux) ? __ldg(a.gout_aux + m * g.ld_daux + n) : 0.f;
+            }
+            v[i] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+            u[i] = make_float4(u4[0], u4[1], u4[2], u4[3]);
+          }
+        }
+      }
+      m_next += 32;
+    };
+
+    gather();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int ks = 0; ks < n_k; ++ks) {
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (active) {
+        uint8_t* base = (is_a ? sA + s * A_BYTES : sB + s * B_BYTES) + (uint32_t)blk * 4096u;
+        constexpr int PLANE_A = A_PLANE, PLANE_B = B_PLANE;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int p = psub + 4 * i;            // position within the stage = K index
+          float4 x;
+          if (is_a) {
+            x = xf4<XFC>(g, v[i], NEED_AUX ? u[i] : make_float4(0.f, 0.f, 0.f, 0.f));
+          } else {
+            x = v[i];
+            if (g.dst_xf != MSMC_XF_NONE) {
+              const float4 ay = gneed_aux ? u[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+              x.x = apply_xf(g.dst_xf, g.dst_slope, x.x, ay.x);
+              x.y = apply_xf(g.dst_xf, g.dst_slope, x.y, ay.y);
+              x.z = apply_xf(g.dst_xf, g.dst_slope, x.z, ay.z);
+              x.w = apply_xf(g.dst_xf, g.dst_slope, x.w, ay.w);
+            }
+            if (do_bias) { bsum[0] += x.x; bsum[1] += x.y; bsum[2] += x.z; bsum[3] += x.w; }
+          }
+          uint8_t* d = base + mn_off(p, chunk);
+          if (SPLIT) {
+            const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+            *reinterpret_cast<float4*>(d) = hi;
+            *reinterpret_cast<float4*>(d + (is_a ? PLANE_A : PLANE_B)) =
+                make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+          } else {
+            *reinterpret_cast<float4*>(d) = x;
+          }
+        }
+      }
+      if (ks + 1 < n_k) gather();
+      fence_proxy_async();
+      mbar_arrive(&full_bar[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+    }
+
+    // ================================= epilogue =================================
+    float* part = a.partial + (int64_t)blockIdx.z * (Ktot * g.Cd + g.Cd);
+    if (do_bias) {
+      // lanes sharing a chunk differ in bits 3 and 4: fixed-order butterfly over the 4 position sub-indices
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t = bsum[j];
+        t += __shfl_xor_sync(0xffffffffu, t, 8);
+        t += __shfl_xor_sync(0xffffffffu, t, 16);
+        const int n = nbase + chunk * 4 + j;
+        if (psub == 0 && n < g.Cd) part[Ktot * g.Cd + n] = t;
+      }
+    }
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    // TMEM lane = accumulator row = (row-block blk, channel lane); warps w and w+4 split the columns
+    const uint32_t taddr = tmem_base + ((uint32_t)(blk * 32) << 16);
+    const int64_t krow = (int64_t)tap * g.Cs + cb * 32 + lane;    // row of dW this thread owns
+    constexpr int CHALF = BN / 2;
+    const int cbeg = (warp >> 2) * CHALF;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + CHALF; c0 += 16) {
+      float acc[16];
+      tmem_ld16(taddr + (uint32_t)c0, acc);
+      if (rb_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < g.Cd) part[krow * g.Cd + n] = acc[j];
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ================================= MMA issuer =================================
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+    if ((tid & 31) == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int ks = 0; ks < n_k; ++ks) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
+        const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+        for (int kg = 0; kg < 4; ++kg) {
+          // one MMA = 8 positions = two 4-row atoms (1 KB) per 32-channel block
+          const uint64_t a_hi = make_desc_mn(a_addr + kg * 1024), b_hi = make_desc_mn(b_addr + kg * 1024);
+          if (SPLIT) {
+            const uint64_t a_lo = make_desc_mn(a_addr + A_PLANE + kg * 1024);
+            const uint64_t b_lo = make_desc_mn(b_addr + B_PLANE + kg * 1024);
+            umma_tf32(tmem_base, a_lo, b_hi, IDESC, (ks > 0 || kg > 0) ? 1u : 0u);
+            umma_tf32(tmem_base, a_hi, b_lo, IDESC, 1u);
+            umma_tf32(tmem_base, a_hi, b_hi, IDESC, 1u);
+          } else {
+            umma_tf32(tmem_base, a_hi, b_hi, IDESC, (ks > 0 || kg > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN)
+                 : "memory");
+  }
+}
+
 // GEMM-layout weight [T][Cs][Cd] (cd contiguous)  ->  swizzled tile images [t'][Cs'/32][n_tile][BN x 128 B]
 //   role 0 (forward)      : n = cd, k = cs, t' = t
 //   role 1 (data gradient): n = cs, k = cd, t' = T-1-t   (stride-1 dgrad == forward conv with reversed taps)
+//   role 2 (data gradient, conv-transpose form): n = cs, k = cd, t' = t
 __global__ void weight_image_kernel(const float* __restrict__ w, float* __restrict__ img, int T, int Cs, int Cd,
                                     int BN, int role, int split) {
   const int Kdim = role ? Cd : Cs;   // reduction channels of this role
@@ -354,7 +756,7 @@ __global__ void weight_image_kernel(const float* __restrict__ w, float* __restri
     const int n = nt * BN + nrow;
     float val = 0.f;
     if (n < Ndim) {
-      const int t = role ? (T - 1 - tp) : tp;
+      const int t = (role == 1) ? (T - 1 - tp) : tp;
       const int cs = role ? n : k, cd = role ? k : n;
       val = w[((int64_t)t * Cs + cs) * Cd + cd];
     }
@@ -373,59 +775,87 @@ __global__ void weight_image_kernel(const float* __restrict__ w, float* __restri
 
 }  // namespace
 
-int umma_pick_bn(int cd) { return cd <= 32 ? 32 : (cd <= 64 ? 64 : 128); }
+// N tile: the widest of {128, 64, 32} that still yields at least ~one CTA per SM (small-M layers such as the
+// FFN / MPD convs would otherwise launch a few dozen CTAs on a 148-SM part)
+int umma_pick_bn(int cd, int64_t rows) {
+  const int64_t mt = ceil_div64(rows, UM_BM);
+  const int64_t want = num_sms();
+  const int cands[3] = {128, 64, 32};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    if (bn > 32 && cd <= bn / 2) continue;               // do not pad N by more than 2x
+    if (mt * ceil_div(cd, bn) >= want || bn == 32) return bn;
+  }
+  return 32;
+}
 
 }  // namespace msmc
 
 using namespace msmc;
 
-extern "C" int msmc_umma_tile_n(int32_t out_channels) { return umma_pick_bn(out_channels); }
+extern "C" int msmc_umma_tile_n(int32_t out_channels, int64_t rows) { return umma_pick_bn(out_channels, rows); }
 
-extern "C" int64_t msmc_weight_image_elems(int32_t T, int32_t Cs, int32_t Cd, int32_t role, int32_t split) {
+extern "C" int64_t msmc_weight_image_elems(int32_t T, int32_t Cs, int32_t Cd, int32_t role, int32_t split,
+                                           int32_t BN) {
   const int Kdim = role ? Cd : Cs, Ndim = role ? Cs : Cd;
-  if (Kdim % 32 != 0) return -1;
-  const int BN = umma_pick_bn(Ndim);
+  if (Kdim % 32 != 0 || (BN != 32 && BN != 64 && BN != 128)) return -1;
   return (int64_t)T * (Kdim / 32) * ceil_div(Ndim, BN) * BN * 32 * (split ? 2 : 1);
 }
 
 extern "C" int msmc_weight_image(const float* w_gemm, float* image, int32_t T, int32_t Cs, int32_t Cd, int32_t role,
-                                 int32_t split, void* stream) {
+                                 int32_t split, int32_t BN, void* stream) {
   MSMC_REQUIRE(w_gemm && image && T > 0 && Cs > 0 && Cd > 0);
-  const int64_t total = msmc_weight_image_elems(T, Cs, Cd, role, 0);
+  const int64_t total = msmc_weight_image_elems(T, Cs, Cd, role, 0, BN);
   MSMC_REQUIRE(total > 0);
-  const int Ndim = role ? Cs : Cd;
   const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 8);
-  weight_image_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_gemm, image, T, Cs, Cd, umma_pick_bn(Ndim), role,
-                                                                split);
+  weight_image_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_gemm, image, T, Cs, Cd, BN, role, split);
   MSMC_CHECK_LAUNCH();
   return MSMC_OK;
 }
 
 extern "C" int msmc_conv_forward_umma(const msmc_conv_geom* gp, const float* src, const float* src_aux,
                                       const float* wimg, const float* bias, const float* residual,
-                                      const float* dst_aux, float* dst, int32_t split, void* stream) {
+                                      const float* dst_aux, float* dst, int32_t split, int32_t BN, void* stream) {
   MSMC_REQUIRE(gp && src && wimg && dst);
   const msmc_conv_geom& g = *gp;
-  MSMC_REQUIRE(!g.transposed);
+  MSMC_REQUIRE(!(g.transposed && g.pad_reflect));
   MSMC_REQUIRE(g.Cs % UM_BK == 0 && g.ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
   MSMC_REQUIRE(!xf_needs_aux(g.src_xf) ||
                (src_aux && g.ld_saux % 4 == 0 && (reinterpret_cast<uintptr_t>(src_aux) & 15) == 0));
   MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || dst_aux);
   MSMC_REQUIRE((reinterpret_cast<uintptr_t>(wimg) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0);
   if (g.pad_reflect) MSMC_REQUIRE((g.ph == 0 || g.ph < g.Hs) && (g.pw == 0 || g.pw < g.Ws));
-  const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
-  const int bn = umma_pick_bn(g.Cd);
-  dim3 grid((unsigned)ceil_div64(M, UM_BM), (unsigned)ceil_div(g.Cd, bn));
+  const int64_t M = g.transposed ? (int64_t)g.B * ceil_div(g.Hd, g.sh) * ceil_div(g.Wd, g.sw)
+                                 : (int64_t)g.B * g.Hd * g.Wd;
+  const int bn = BN;
+  MSMC_REQUIRE(bn == 32 || bn == 64 || bn == 128);
+  if (g.transposed) MSMC_REQUIRE(ceil_div(g.KH, g.sh) * ceil_div(g.KW, g.sw) <= UM_MAX_PHASE_TAPS);
+  dim3 grid((unsigned)ceil_div64(M, UM_BM), (unsigned)ceil_div(g.Cd, bn),
+            (unsigned)(g.transposed ? g.sh * g.sw : 1));
   UmmaArgs a;
   a.g = g; a.src = src; a.src_aux = src_aux; a.wimg = wimg; a.bias = bias; a.residual = residual;
   a.dst_aux = dst_aux; a.dst = dst;
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH_UMMA(BN_, SPLIT_, ST_)                                                                            \
+  const int xfc = g.src_xf == MSMC_XF_NONE ? XFC_NONE
+                  : (g.src_xf == MSMC_XF_LRELU && g.src_slope > 0.f && g.src_slope < 1.f) ? XFC_LRELU : XFC_GENERIC;
+#define LAUNCH_UMMA_X(BN_, SPLIT_, ST_, X_)                                                                      \
   do {                                                                                                           \
     const size_t smem = 1024 + (size_t)ST_ * (SPLIT_ ? 2 : 1) * (UM_BM * 128 + BN_ * 128) + (2 * ST_ + 1) * 8 + 16; \
-    cudaFuncSetAttribute(conv_umma_kernel<BN_, SPLIT_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                         (int)smem);                                                                             \
-    conv_umma_kernel<BN_, SPLIT_, ST_><<<grid, UM_THREADS, smem, st>>>(a);                                       \
+    if (g.transposed) {                                                                                          \
+      cudaFuncSetAttribute(conv_umma_kernel<BN_, SPLIT_, ST_, X_, true>,                                         \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              \
+      conv_umma_kernel<BN_, SPLIT_, ST_, X_, true><<<grid, UMF_THREADS, smem, st>>>(a);                          \
+    } else {                                                                                                     \
+      cudaFuncSetAttribute(conv_umma_kernel<BN_, SPLIT_, ST_, X_, false>,                                        \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              \
+      conv_umma_kernel<BN_, SPLIT_, ST_, X_, false><<<grid, UMF_THREADS, smem, st>>>(a);                         \
+    }                                                                                                            \
+  } while (0)
+#define LAUNCH_UMMA(BN_, SPLIT_, ST_)                                \
+  do {                                                               \
+    if (xfc == XFC_NONE) LAUNCH_UMMA_X(BN_, SPLIT_, ST_, XFC_NONE);  \
+    else if (xfc == XFC_LRELU) LAUNCH_UMMA_X(BN_, SPLIT_, ST_, XFC_LRELU); \
+    else LAUNCH_UMMA_X(BN_, SPLIT_, ST_, XFC_GENERIC);               \
   } while (0)
   if (split) {
     switch (bn) {
@@ -441,6 +871,90 @@ extern "C" int msmc_conv_forward_umma(const msmc_conv_geom* gp, const float* src
     }
   }
 #undef LAUNCH_UMMA
+#undef LAUNCH_UMMA_X
   MSMC_CHECK_LAUNCH();
   return MSMC_OK;
+}
+
+namespace {
+int umma_wgrad_bn(int cd) { return cd <= 32 ? 32 : (cd <= 64 ? 64 : 128); }
+int umma_wgrad_splits(const msmc_conv_geom& g, int bn) {
+  const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
+  const int RB = g.KH * g.KW * (g.Cs / 32);
+  const int64_t tiles = (int64_t)ceil_div(RB, 4) * ceil_div(g.Cd, bn);
+  int64_t s = ceil_div64((int64_t)num_sms() * 2, tiles);
+  const int64_t max_by_rows = std::max<int64_t>(1, M / 256);      // at least 8 stages per CTA
+  if (s > max_by_rows) s = max_by_rows;
+  const int64_t per = ((int64_t)g.KH * g.KW * g.Cs * g.Cd + g.Cd) * (int64_t)sizeof(float);
+  const int64_t cap = ((int64_t)128 << 20) / per;
+  if (s > cap) s = cap;
+  return (int)std::max<int64_t>(1, s);
+}
+}  // namespace
+
+extern "C" int64_t msmc_conv_wgrad_umma_workspace(const msmc_conv_geom* gp) {
+  if (!gp || gp->Cs % 32 != 0) return -1;
+  const msmc_conv_geom& g = *gp;
+  const int bn = umma_wgrad_bn(g.Cd);
+  return (int64_t)umma_wgrad_splits(g, bn) * ((int64_t)g.KH * g.KW * g.Cs * g.Cd + g.Cd) * (int64_t)sizeof(float);
+}
+
+extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, const float* src_aux,
+                                    const float* gout, const float* gout_aux, float* dw, float* dbias,
+                                    float* workspace, int64_t workspace_bytes, int32_t split, void* stream) {
+  MSMC_REQUIRE(gp && src && gout && dw && workspace);
+  const msmc_conv_geom& g = *gp;
+  MSMC_REQUIRE(!g.transposed && g.Cs % 32 == 0 && g.ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  MSMC_REQUIRE(!xf_needs_aux(g.src_xf) ||
+               (src_aux && g.ld_saux % 4 == 0 && (reinterpret_cast<uintptr_t>(src_aux) & 15) == 0));
+  MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || gout_aux);
+  const int bn = umma_wgrad_bn(g.Cd);
+  const int splits = umma_wgrad_splits(g, bn);
+  const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
+  MSMC_REQUIRE(workspace_bytes >= (int64_t)splits * (Ktot * g.Cd + g.Cd) * (int64_t)sizeof(float));
+  const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
+  UmmaWgradArgs a;
+  a.g = g; a.src = src; a.src_aux = src_aux; a.gout = gout; a.gout_aux = gout_aux; a.partial = workspace;
+  a.rows_per_split = ceil_div64(ceil_div64(M, splits), 32) * 32;
+  a.want_bias = dbias != nullptr;
+  a.gvec = (g.ld_dst % 4 == 0) && (reinterpret_cast<uintptr_t>(gout) & 15) == 0 &&
+           (!xf_needs_aux(g.dst_xf) || ((g.ld_daux % 4 == 0) && (reinterpret_cast<uintptr_t>(gout_aux) & 15) == 0));
+  // every split must own at least one position so that each partial tile is written
+  const int eff_splits = (int)ceil_div64(M, a.rows_per_split);
+  const int RB = g.KH * g.KW * (g.Cs / 32);
+  dim3 grid((unsigned)ceil_div(RB, 4), (unsigned)ceil_div(g.Cd, bn), (unsigned)eff_splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int xfc = g.src_xf == MSMC_XF_NONE ? XFC_NONE
+                  : (g.src_xf == MSMC_XF_LRELU && g.src_slope > 0.f && g.src_slope < 1.f) ? XFC_LRELU : XFC_GENERIC;
+#define LAUNCH_WG_X(BN_, SPLIT_, ST_, X_)                                                                       \
+  do {                                                                                                          \
+    const size_t smem = 1024 + (size_t)ST_ * (SPLIT_ ? 2 : 1) * (4 * 4096 + (BN_ / 32) * 4096) +                \
+                        (2 * ST_ + 1) * 8 + 16;                                                                 \
+    cudaFuncSetAttribute(conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_>,                                          \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                               \
+    conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_><<<grid, UMF_THREADS, smem, st>>>(a);                           \
+  } while (0)
+#define LAUNCH_WG(BN_, SPLIT_, ST_)                                        \
+  do {                                                                     \
+    if (xfc == XFC_NONE) LAUNCH_WG_X(BN_, SPLIT_, ST_, XFC_NONE);          \
+    else if (xfc == XFC_LRELU) LAUNCH_WG_X(BN_, SPLIT_, ST_, XFC_LRELU);   \
+    else LAUNCH_WG_X(BN_, SPLIT_, ST_, XFC_GENERIC);                       \
+  } while (0)
+  if (split) {
+    switch (bn) {
+      case 32: LAUNCH_WG(32, true, 4); break;
+      case 64: LAUNCH_WG(64, true, 4); break;
+      default: LAUNCH_WG(128, true, 3); break;
+    }
+  } else {
+    switch (bn) {
+      case 32: LAUNCH_WG(32, false, 4); break;
+      case 64: LAUNCH_WG(64, false, 4); break;
+      default: LAUNCH_WG(128, false, 4); break;
+    }
+  }
+#undef LAUNCH_WG
+#undef LAUNCH_WG_X
+  MSMC_CHECK_LAUNCH();
+  return launch_wgrad_reduce(g, workspace, eff_splits, dw, dbias, stream);
 }

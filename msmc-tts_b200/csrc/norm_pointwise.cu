@@ -153,32 +153,38 @@ __global__ void colsum_partials_kernel(const float* __restrict__ partial, int np
 
 // ---------------------------------------------------------------------------------------------- spectral
 __global__ void spec_mag_fwd_kernel(const float* __restrict__ spec, float* __restrict__ mag, int64_t rows,
-                                    int F, float floor_, int floor_add) {
+                                    int F, int Fp, float floor_, int floor_add) {
   const int64_t total = rows * F;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = e / F;
     const int f = (int)(e - r * F);
-    const float re = spec[r * 2 * F + f], im = spec[r * 2 * F + F + f];
+    const float re = spec[r * 2 * Fp + f], im = spec[r * 2 * Fp + Fp + f];
     const float p = re * re + im * im;
     mag[e] = sqrtf(floor_add ? p + floor_ : fmaxf(p, floor_));
   }
 }
 __global__ void spec_mag_bwd_kernel(const float* __restrict__ gmag, const float* __restrict__ spec,
                                     const float* __restrict__ mag, float* __restrict__ gspec, int64_t rows,
-                                    int F, float floor_, int floor_add) {
-  const int64_t total = rows * F;
+                                    int F, int Fp, float floor_, int floor_add) {
+  // one thread per (row, padded bin): the padding columns of the gradient are written as zeros
+  const int64_t total = rows * Fp;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = e / F;
-    const int f = (int)(e - r * F);
-    const float re = spec[r * 2 * F + f], im = spec[r * 2 * F + F + f];
-    const float p = re * re + im * im;
-    // d sqrt(u)/du = 1/(2 sqrt(u)); clamp passes gradient only where p >= floor
-    float c = 0.f;
-    if (floor_add || p >= floor_) c = gmag[e] / mag[e];
-    gspec[r * 2 * F + f] = c * re;
-    gspec[r * 2 * F + F + f] = c * im;
+    const int64_t r = e / Fp;
+    const int f = (int)(e - r * Fp);
+    float gre = 0.f, gim = 0.f;
+    if (f < F) {
+      const float re = spec[r * 2 * Fp + f], im = spec[r * 2 * Fp + Fp + f];
+      const float p = re * re + im * im;
+      // d sqrt(u)/du = 1/(2 sqrt(u)); clamp passes gradient only where p >= floor
+      float c = 0.f;
+      if (floor_add || p >= floor_) c = gmag[r * F + f] / mag[r * F + f];
+      gre = c * re;
+      gim = c * im;
+    }
+    gspec[r * 2 * Fp + f] = gre;
+    gspec[r * 2 * Fp + Fp + f] = gim;
   }
 }
 
@@ -247,6 +253,31 @@ __global__ void gated_act_bwd_kernel(const float* __restrict__ gy, const float* 
   }
 }
 
+// Backward of reflect-padded STFT framing: per-frame time-domain gradients (B, frames, win) are overlap-added onto
+// the padded time axis and the reflected borders folded back in one pass:
+//   gx[b, l] = sum_{p in preimage(l)} sum_{f : 0 <= p - f*hop < win} gframes[b, f, p - f*hop]
+__global__ void overlap_add_fold_kernel(const float* __restrict__ gf, float* __restrict__ gx, int B, int frames,
+                                        int win, int hop, int L, int pad) {
+  const int64_t total = (int64_t)B * L;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e / L), l = (int)(e - (int64_t)b * L);
+    int pc[3], np = 0;
+    pc[np++] = l + pad;
+    if (l >= 1 && l <= pad) pc[np++] = pad - l;
+    if (l <= L - 2 && l >= L - 1 - pad) pc[np++] = pad + 2 * (L - 1) - l;
+    float s = 0.f;
+    for (int i = 0; i < np; ++i) {
+      const int p = pc[i];
+      int f_hi = p / hop;                       // largest f with f*hop <= p
+      if (f_hi > frames - 1) f_hi = frames - 1;
+      for (int f = f_hi; f >= 0 && p - f * hop < win; --f)
+        s += gf[((int64_t)b * frames + f) * win + (p - f * hop)];
+    }
+    gx[e] = s;
+  }
+}
+
 inline int ew_blocks(int64_t n) { return (int)std::min<int64_t>(ceil_div64(n, 256), (int64_t)num_sms() * 16); }
 
 constexpr int LN_BWD_MAX_BLOCKS = 296;
@@ -307,18 +338,20 @@ extern "C" int msmc_add_layernorm_bwd(const float* gy, const float* xhat, const 
   return MSMC_OK;
 }
 
-extern "C" int msmc_spec_magnitude_fwd(const float* spec, float* mag, int64_t rows, int32_t F, float floor_,
-                                       int32_t floor_add, void* stream) {
-  MSMC_REQUIRE(spec && mag && rows > 0 && F > 0);
-  spec_mag_fwd_kernel<<<ew_blocks(rows * F), 256, 0, (cudaStream_t)stream>>>(spec, mag, rows, F, floor_, floor_add);
+extern "C" int msmc_spec_magnitude_fwd(const float* spec, float* mag, int64_t rows, int32_t F, int32_t Fp,
+                                       float floor_, int32_t floor_add, void* stream) {
+  MSMC_REQUIRE(spec && mag && rows > 0 && F > 0 && Fp >= F);
+  spec_mag_fwd_kernel<<<ew_blocks(rows * F), 256, 0, (cudaStream_t)stream>>>(spec, mag, rows, F, Fp, floor_,
+                                                                             floor_add);
   MSMC_CHECK_LAUNCH();
   return MSMC_OK;
 }
 extern "C" int msmc_spec_magnitude_bwd(const float* gmag, const float* spec, const float* mag, float* gspec,
-                                       int64_t rows, int32_t F, float floor_, int32_t floor_add, void* stream) {
-  MSMC_REQUIRE(gmag && spec && mag && gspec && rows > 0 && F > 0);
-  spec_mag_bwd_kernel<<<ew_blocks(rows * F), 256, 0, (cudaStream_t)stream>>>(gmag, spec, mag, gspec, rows, F,
-                                                                             floor_, floor_add);
+                                       int64_t rows, int32_t F, int32_t Fp, float floor_, int32_t floor_add,
+                                       void* stream) {
+  MSMC_REQUIRE(gmag && spec && mag && gspec && rows > 0 && F > 0 && Fp >= F);
+  spec_mag_bwd_kernel<<<ew_blocks(rows * Fp), 256, 0, (cudaStream_t)stream>>>(gmag, spec, mag, gspec, rows, F, Fp,
+                                                                              floor_, floor_add);
   MSMC_CHECK_LAUNCH();
   return MSMC_OK;
 }
@@ -346,6 +379,14 @@ extern "C" int msmc_log_clamp_bwd(const float* gy, const float* x, float* gx, in
                                   void* stream) {
   MSMC_REQUIRE(gy && x && gx && n > 0);
   log_clamp_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(gy, x, gx, n, clip);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+extern "C" int msmc_overlap_add_fold(const float* gframes, float* gx, int32_t B, int32_t frames, int32_t win,
+                                     int32_t hop, int32_t L, int32_t pad, void* stream) {
+  MSMC_REQUIRE(gframes && gx && B > 0 && frames > 0 && win > 0 && hop > 0 && L > 0 && pad >= 0 && pad < L);
+  overlap_add_fold_kernel<<<ew_blocks((int64_t)B * L), 256, 0, (cudaStream_t)stream>>>(gframes, gx, B, frames, win,
+                                                                                      hop, L, pad);
   MSMC_CHECK_LAUNCH();
   return MSMC_OK;
 }

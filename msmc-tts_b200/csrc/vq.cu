@@ -3,9 +3,9 @@
 // (reference vqgantts/modules.py:24-67, 86-116, 137-169).
 //
 // Search kernel: the head's codebook (dim x K, dim-major, exactly the reference's `embed` buffer) is staged in
-// shared memory once per CTA together with ||e_k||^2; one warp owns one row at a time, lane l scores codewords
-// l, l+32, ... with the row broadcast by warp shuffle, and the argmin is a warp-shuffle reduction (lowest index
-// wins ties).  Distances use the reference's expanded form (||z||^2 - 2 z.e_k) + ||e_k||^2 in true fp32 with a
+// shared memory once per CTA together with ||e_k||^2; one warp scores 4 rows at a time, lane l holding 4*KQ
+// consecutive-by-4 codewords (one LDS.128 feeds 16 FMAs) with the rows broadcast by warp shuffle, and the argmin is
+// a warp-shuffle reduction (lowest index wins ties).  Distances use the reference's expanded form (||z||^2 - 2 z.e_k) + ||e_k||^2 in true fp32 with a
 // fixed, sequential fma order that the C oracle (oracle/vq_oracle.c) reproduces bit for bit.
 // HBM-bound integer/float gather work: no tensor cores.
 #include "common.cuh"
@@ -15,16 +15,21 @@ namespace msmc {
 namespace {
 
 constexpr int VQ_WARPS = 8;
-constexpr int MAX_KPL = 16;  // codewords per lane -> n_embed <= 512
 
-template <int DIM, int KPL>
+// VEC codewords per lane per 16-byte shared-memory load, KQ such loads per dim: the CTA's padded codebook width is
+// Kp = 32 * VEC * KQ >= K (padding codewords get distance +inf).  Each warp scores R = 4 rows at once so one
+// LDS.128 of the codebook feeds 16 FMAs.
+constexpr int VQ_R = 4;
+
+template <int DIM, int VEC, int KQ>
 __global__ void __launch_bounds__(VQ_WARPS * 32)
 vq_search_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restrict__ embed,
                  float* __restrict__ quant_raw, float* __restrict__ quant_st, float* __restrict__ diff,
                  int64_t* __restrict__ idx, int n_rows, int n_heads, int K, int rows_per_cta) {
-  extern __shared__ float smem[];
-  float* cb = smem;                  // [DIM][K]
-  float* ee = smem + (size_t)DIM * K;  // [K]
+  extern __shared__ __align__(16) float smem[];
+  constexpr int KP = 32 * VEC * KQ;
+  float* cb = smem;                      // [DIM][KP]
+  float* ee = smem + (size_t)DIM * KP;   // [KP]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_beg = blockIdx.x * rows_per_cta;
   const int row_end = min(n_rows, row_beg + rows_per_cta);
@@ -34,72 +39,102 @@ vq_search_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restr
   for (int h = 0; h < n_heads; ++h) {
     __syncthreads();  // previous head's codebook fully consumed
     const float* e_h = embed + (size_t)h * DIM * K;
-    for (int i = threadIdx.x; i < DIM * K; i += blockDim.x) cb[i] = e_h[i];
+    for (int i = threadIdx.x; i < DIM * KP; i += blockDim.x) {
+      const int d = i / KP, k = i - d * KP;
+      cb[i] = (k < K) ? e_h[(size_t)d * K + k] : 0.f;
+    }
     __syncthreads();
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    for (int k = threadIdx.x; k < KP; k += blockDim.x) {
       float s = 0.f;
 #pragma unroll 8
-      for (int d = 0; d < DIM; ++d) { float v = cb[d * K + k]; s = fmaf(v, v, s); }
-      ee[k] = s;
+      for (int d = 0; d < DIM; ++d) { float v = cb[d * KP + k]; s = fmaf(v, v, s); }
+      ee[k] = (k < K) ? s : INFINITY;
     }
     __syncthreads();
 
-    for (int r = row_beg + warp; r < row_end; r += VQ_WARPS) {
-      const float* zr = z + (int64_t)r * ld_z + h * DIM;
-      float zl[DPL];
+    for (int r0 = row_beg + warp * VQ_R; r0 < row_end; r0 += VQ_WARPS * VQ_R) {
+      float zl[VQ_R][DPL];
 #pragma unroll
-      for (int j = 0; j < DPL; ++j) zl[j] = zr[lane + 32 * j];
-      float dot[KPL];
+      for (int r = 0; r < VQ_R; ++r) {
+        const int row = min(r0 + r, row_end - 1);       // tail rows are recomputed, never stored twice
+        const float* zr = z + (int64_t)row * ld_z + h * DIM;
 #pragma unroll
-      for (int j = 0; j < KPL; ++j) dot[j] = 0.f;
-      float zz = 0.f;
+        for (int j = 0; j < DPL; ++j) zl[r][j] = zr[lane + 32 * j];
+      }
+      float dot[VQ_R][KQ * VEC];
+      float zz[VQ_R];
+#pragma unroll
+      for (int r = 0; r < VQ_R; ++r) {
+        zz[r] = 0.f;
+#pragma unroll
+        for (int c = 0; c < KQ * VEC; ++c) dot[r][c] = 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < DPL; ++j) {
-#pragma unroll 8
+#pragma unroll 4
         for (int dl = 0; dl < 32; ++dl) {
-          // sequential over d = 32*j + dl: every lane sees the same broadcast value
-          const float zd = __shfl_sync(0xffffffffu, zl[j], dl);
-          zz = fmaf(zd, zd, zz);
-          const float* cr = cb + (size_t)(32 * j + dl) * K + lane;
+          // sequential over d = 32*j + dl, identical order to oracle/vq_oracle.c
+          float ev[KQ * VEC];
+          const float* cr = cb + (size_t)(32 * j + dl) * KP + lane * VEC;
 #pragma unroll
-          for (int q = 0; q < KPL; ++q) {
-            const int k = lane + 32 * q;
-            if (k < K) dot[q] = fmaf(zd, cr[32 * q], dot[q]);
+          for (int q = 0; q < KQ; ++q) {
+            if (VEC == 4) {
+              const float4 t = *reinterpret_cast<const float4*>(cr + q * 32 * VEC);
+              ev[q * VEC + 0] = t.x; ev[q * VEC + 1] = t.y; ev[q * VEC + 2] = t.z; ev[q * VEC + 3] = t.w;
+            } else if (VEC == 2) {
+              const float2 t = *reinterpret_cast<const float2*>(cr + q * 32 * VEC);
+              ev[q * VEC + 0] = t.x; ev[q * VEC + 1] = t.y;
+            } else {
+              ev[q * VEC] = cr[q * 32 * VEC];
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < VQ_R; ++r) {
+            const float zd = __shfl_sync(0xffffffffu, zl[r][j], dl);
+            zz[r] = fmaf(zd, zd, zz[r]);
+#pragma unroll
+            for (int c = 0; c < KQ * VEC; ++c) dot[r][c] = fmaf(zd, ev[c], dot[r][c]);
           }
         }
       }
-      float best = INFINITY;
-      int best_k = 0x7fffffff;
 #pragma unroll
-      for (int q = 0; q < KPL; ++q) {
-        const int k = lane + 32 * q;
-        if (k < K) {
-          const float dist = (zz - 2.f * dot[q]) + ee[k];
-          if (dist < best || (dist == best && k < best_k)) { best = dist; best_k = k; }
+      for (int r = 0; r < VQ_R; ++r) {
+        const int row = r0 + r;
+        float best = INFINITY;
+        int best_k = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < KQ; ++q)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const int k = q * 32 * VEC + lane * VEC + v;
+            const float dist = (zz[r] - 2.f * dot[r][q * VEC + v]) + ee[k];
+            if (dist < best || (dist == best && k < best_k)) { best = dist; best_k = k; }
+          }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+          if (ob < best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
         }
-      }
+        if (row < row_end) {
+          if (lane == 0) idx[(int64_t)row * n_heads + h] = (int64_t)best_k;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
-        if (ob < best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
-      }
-      if (lane == 0) idx[(int64_t)r * n_heads + h] = (int64_t)best_k;
-#pragma unroll
-      for (int j = 0; j < DPL; ++j) {
-        const int d = lane + 32 * j;
-        const float q = cb[d * K + best_k];
-        const float x = zl[j];
-        const int64_t o = (int64_t)r * (n_heads * DIM) + h * DIM + d;
-        quant_raw[o] = q;
-        quant_st[o] = x + (q - x);
-        const float dq = q - x;
-        const float dv = __fmul_rn(dq, dq);   // no fma contraction with the head sum below (matches the C oracle)
-        float* dp = diff + (int64_t)r * DIM + d;
-        // sum over heads in head order (python `sum(diffs)`), then / n_heads
-        float acc = (h == 0) ? dv : __fadd_rn(*dp, dv);
-        if (h == n_heads - 1) acc *= inv_heads;
-        *dp = acc;
+          for (int j = 0; j < DPL; ++j) {
+            const int d = lane + 32 * j;
+            const float q = cb[d * KP + best_k];
+            const float x = zl[r][j];
+            const int64_t o = (int64_t)row * (n_heads * DIM) + h * DIM + d;
+            quant_raw[o] = q;
+            quant_st[o] = x + (q - x);
+            const float dq = q - x;
+            const float dv = __fmul_rn(dq, dq);   // no fma contraction with the head sum below (matches the C oracle)
+            float* dp = diff + (int64_t)row * DIM + d;
+            // sum over heads in head order (python `sum(diffs)`), then / n_heads
+            float acc = (h == 0) ? dv : __fadd_rn(*dp, dv);
+            if (h == n_heads - 1) acc *= inv_heads;
+            *dp = acc;
+          }
+        }
       }
     }
   }
@@ -281,30 +316,38 @@ extern "C" int msmc_vq_search(const float* z, int64_t ld_z, const float* embed, 
                               float* quant_st, float* diff, int64_t* idx, int32_t n_rows, int32_t n_heads,
                               int32_t dim, int32_t n_embed, void* stream) {
   MSMC_REQUIRE(z && embed && quant_raw && quant_st && diff && idx);
-  MSMC_REQUIRE(n_rows > 0 && n_heads > 0 && n_embed > 0 && n_embed <= 32 * MAX_KPL);
+  MSMC_REQUIRE(n_rows > 0 && n_heads > 0 && n_embed > 0 && n_embed <= 512);
   if (dim != 64 && dim != 32 && dim != 128 && dim != 256) return MSMC_ERR_UNSUPPORTED;
-  const size_t smem = ((size_t)dim * n_embed + n_embed) * sizeof(float);
+  // padded codebook width Kp = 32 * VEC * KQ
+  int vec, kq;
+  if (n_embed <= 32) { vec = 1; kq = 1; }
+  else if (n_embed <= 64) { vec = 2; kq = 1; }
+  else if (n_embed <= 128) { vec = 4; kq = 1; }
+  else if (n_embed <= 256) { vec = 4; kq = 2; }
+  else { vec = 4; kq = 4; }
+  const int kp = 32 * vec * kq;
+  const size_t smem = ((size_t)dim * kp + kp) * sizeof(float);
   if (smem > 200 * 1024) return MSMC_ERR_UNSUPPORTED;
-  // fill the machine: at least 8 rows (one per warp) per CTA, at most ~2 CTAs per SM in flight
-  int rows_per_cta = std::max(VQ_WARPS, (int)ceil_div(n_rows, 2 * num_sms()));
-  rows_per_cta = ceil_div(rows_per_cta, VQ_WARPS) * VQ_WARPS;
+  // one CTA per SM where possible; a warp handles VQ_R rows per pass
+  const int quantum = VQ_WARPS * VQ_R;
+  int rows_per_cta = std::max(quantum, (int)ceil_div(n_rows, num_sms()));
+  rows_per_cta = ceil_div(rows_per_cta, quantum) * quantum;
   const int grid = ceil_div(n_rows, rows_per_cta);
   cudaStream_t st = (cudaStream_t)stream;
-  const int kpl = ceil_div(n_embed, 32);
-#define LAUNCH_VQ2(D, Q)                                                                                    \
-  do {                                                                                                      \
-    if (smem > 48 * 1024)                                                                                   \
-      cudaFuncSetAttribute(vq_search_kernel<D, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    vq_search_kernel<D, Q><<<grid, VQ_WARPS * 32, smem, st>>>(z, ld_z, embed, quant_raw, quant_st, diff,   \
-                                                               idx, n_rows, n_heads, n_embed, rows_per_cta);\
+#define LAUNCH_VQ3(D, V, Q)                                                                                   \
+  do {                                                                                                        \
+    if (smem > 48 * 1024)                                                                                     \
+      cudaFuncSetAttribute(vq_search_kernel<D, V, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    vq_search_kernel<D, V, Q><<<grid, VQ_WARPS * 32, smem, st>>>(z, ld_z, embed, quant_raw, quant_st, diff,  \
+                                                                  idx, n_rows, n_heads, n_embed, rows_per_cta);\
   } while (0)
-#define LAUNCH_VQ(D)                                  \
-  do {                                                \
-    if (kpl <= 1) LAUNCH_VQ2(D, 1);                   \
-    else if (kpl <= 2) LAUNCH_VQ2(D, 2);              \
-    else if (kpl <= 4) LAUNCH_VQ2(D, 4);              \
-    else if (kpl <= 8) LAUNCH_VQ2(D, 8);              \
-    else LAUNCH_VQ2(D, 16);                           \
+#define LAUNCH_VQ(D)                                    \
+  do {                                                  \
+    if (vec == 1) LAUNCH_VQ3(D, 1, 1);                  \
+    else if (vec == 2) LAUNCH_VQ3(D, 2, 1);             \
+    else if (kq == 1) LAUNCH_VQ3(D, 4, 1);              \
+    else if (kq == 2) LAUNCH_VQ3(D, 4, 2);              \
+    else LAUNCH_VQ3(D, 4, 4);                           \
   } while (0)
   switch (dim) {
     case 32: LAUNCH_VQ(32); break;
@@ -313,7 +356,7 @@ extern "C" int msmc_vq_search(const float* z, int64_t ld_z, const float* embed, 
     default: LAUNCH_VQ(256); break;
   }
 #undef LAUNCH_VQ
-#undef LAUNCH_VQ2
+#undef LAUNCH_VQ3
   MSMC_CHECK_LAUNCH();
   return MSMC_OK;
 }

@@ -49,18 +49,18 @@ def conv_out_size(n, k, s, d, p, transposed):
     return (n + 2 * p - d * (k - 1) - 1) // s + 1
 
 
-def _weight_image(w, T, Cs, Cd, role, split):
+def _weight_image(w, T, Cs, Cd, role, split, bn):
     """swizzled tcgen05 operand image of a GEMM-layout weight [T][Cs][Cd]; cached on the tensor for its lifetime"""
     cache = getattr(w, "_msmc_img", None)
     if cache is None:
         cache = {}
         w._msmc_img = cache
-    key = (role, split)
+    key = (role, split, bn)
     img = cache.get(key)
     if img is None:
-        n = L.load().msmc_weight_image_elems(T, Cs, Cd, role, split)
+        n = L.load().msmc_weight_image_elems(T, Cs, Cd, role, split, bn)
         img = torch.empty(n, dtype=torch.float32, device=w.device)
-        L.call("msmc_weight_image", L.ptr(w), L.ptr(img), T, Cs, Cd, role, split)
+        L.call("msmc_weight_image", L.ptr(w), L.ptr(img), T, Cs, Cd, role, split, bn)
         cache[key] = img
     return img
 
@@ -109,14 +109,15 @@ def _launch_conv(src, w, wstr, bias, residual, dst, KH, KW, sh, sw, dh, dw, ph, 
         meta = {"flops": 2.0 * pos * KH * KW * Cs * Cd,
                 "bytes": 4.0 * (src.numel() + dst.numel() + KH * KW * Cs * Cd + (res.numel() if res is not None else 0)),
                 "shape": "B%d %dx%d C%d->%d k%dx%d s%d%s" % (B, Hs, Ws, Cs, Cd, KH, KW, sw, "T" if transposed else "")}
-    gemm_contig = (not transposed) and tuple(wstr) == (KW * Cs * Cd, Cs * Cd, Cd, 1)
-    if w_role == 1 or (gemm_contig and _umma_ok(src, ld_src, w, (Cs, Cd), KH, KW, Cs, Cd, B * Hd * Wd, saux,
+    gemm_contig = tuple(wstr) == (KW * Cs * Cd, Cs * Cd, Cd, 1) and not (transposed and reflect)
+    if w_role != 0 or (gemm_contig and _umma_ok(src, ld_src, w, (Cs, Cd), KH, KW, Cs, Cd, B * Hd * Wd, saux,
                                                   g.ld_saux)):
         split = 0 if CONV_MATH == "tf32" else 1
-        cs_op, cd_op = w_dims if w_role == 1 else (Cs, Cd)
-        img = _weight_image(w, KH * KW, cs_op, cd_op, w_role, split)
+        cs_op, cd_op = w_dims if w_role != 0 else (Cs, Cd)
+        bn = L.load().msmc_umma_tile_n(Cd, B * Hd * Wd)
+        img = _weight_image(w, KH * KW, cs_op, cd_op, w_role, split, bn)
         L.call("msmc_conv_forward_umma", C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(img), L.ptr(bias), L.ptr(res),
-               L.ptr(daux), L.ptr(dst), split, meta=meta)
+               L.ptr(daux), L.ptr(dst), split, bn, meta=meta)
         return dst
     L.call("msmc_conv_forward", C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(w), L.ptr(bias), L.ptr(res),
            L.ptr(daux), L.ptr(dst), meta=meta)
@@ -144,13 +145,22 @@ def _launch_wgrad(src, gout, dw, wstr, dbias, KH, KW, sh, sw, dh, dw_, ph, pw, r
     g.src_xf, g.src_slope = src_xf[0], float(src_xf[1])
     g.dst_xf, g.dst_slope = gout_xf[0], float(gout_xf[1])
     lib = L.load()
-    nbytes = lib.msmc_conv_wgrad_workspace(C.byref(g))
-    ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=src.device)
     meta = None
     if L._profile is not None:
         meta = {"flops": 2.0 * B * Hd * Wd * KH * KW * Cs * Cd,
                 "bytes": 4.0 * (src.numel() + gout.numel() + KH * KW * Cs * Cd),
                 "shape": "wgrad B%d %dx%d C%d->%d k%dx%d" % (B, Hs, Ws, Cs, Cd, KH, KW)}
+    use_umma = (CONV_MATH != "fp32" and Cs % 32 == 0 and ld_src % 4 == 0 and src.data_ptr() % 16 == 0
+                and B * Hd * Wd >= UMMA_MIN_ROWS
+                and (saux is None or (g.ld_saux % 4 == 0 and saux.data_ptr() % 16 == 0)))
+    if use_umma:
+        nbytes = lib.msmc_conv_wgrad_umma_workspace(C.byref(g))
+        ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=src.device)
+        L.call("msmc_conv_wgrad_umma", C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(gout), L.ptr(daux), L.ptr(dw),
+               L.ptr(dbias), L.ptr(ws), C.c_int64(nbytes), 0 if CONV_MATH == "tf32" else 1, meta=meta)
+        return
+    nbytes = lib.msmc_conv_wgrad_workspace(C.byref(g))
+    ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=src.device)
     L.call("msmc_conv_wgrad", C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(gout), L.ptr(daux), L.ptr(dw),
            L.ptr(dbias), L.ptr(ws), C.c_int64(nbytes), meta=meta)
 
@@ -201,8 +211,24 @@ class _ConvFn(torch.autograd.Function):
                 # gradient w.r.t. the reflect-padded input, then fold the borders back
                 B, Hs, Ws, Cs = x.shape
                 gpad = torch.empty((B, Hs + 2 * cfg.ph, Ws + 2 * cfg.pw, Cs), dtype=torch.float32, device=x.device)
-                _launch_conv(gy, w, (s_kh, s_kw, s_cd, s_cs), None, None, gpad, cfg.KH, cfg.KW, cfg.sh, cfg.sw,
-                             cfg.dh, cfg.dw, 0, 0, False, True, src_xf=gmod)
+                gy_r, ld_gy = _rows(gy)
+                aux_r, ld_aux = _rows(gmod[2]) if gmod[2] is not None else (None, 0)
+                if (cfg.sh == 1 and cfg.sw == 1 and cfg.wstr == (cfg.KW * Cs * cfg.Cd, Cs * cfg.Cd, cfg.Cd, 1)
+                        and _umma_ok(gy_r, ld_gy, w, (Cs, cfg.Cd), cfg.KH, cfg.KW, cfg.Cd, Cs,
+                                     gpad.shape[0] * gpad.shape[1] * gpad.shape[2], aux_r, ld_aux)):
+                    # stride 1: full correlation with reversed taps on the tensor cores
+                    _launch_conv(gy, w, (cfg.KW * cfg.Cd * Cs, cfg.Cd * Cs, Cs, 1), None, None, gpad, cfg.KH, cfg.KW,
+                                 1, 1, cfg.dh, cfg.dw, cfg.dh * (cfg.KH - 1), cfg.dw * (cfg.KW - 1), False, False,
+                                 src_xf=gmod, w_role=1, w_dims=(Cs, cfg.Cd))
+                elif (cfg.wstr == (cfg.KW * Cs * cfg.Cd, Cs * cfg.Cd, cfg.Cd, 1)
+                      and _umma_ok(gy_r, ld_gy, w, (Cs, cfg.Cd), cfg.KH, cfg.KW, cfg.Cd, Cs,
+                                   gpad.shape[0] * gpad.shape[1] * gpad.shape[2], aux_r, ld_aux)):
+                    # strided: conv-transpose form on the tensor cores (phase-decomposed)
+                    _launch_conv(gy, w, (s_kh, s_kw, s_cd, s_cs), None, None, gpad, cfg.KH, cfg.KW, cfg.sh, cfg.sw,
+                                 cfg.dh, cfg.dw, 0, 0, False, True, src_xf=gmod, w_role=2, w_dims=(Cs, cfg.Cd))
+                else:
+                    _launch_conv(gy, w, (s_kh, s_kw, s_cd, s_cs), None, None, gpad, cfg.KH, cfg.KW, cfg.sh, cfg.sw,
+                                 cfg.dh, cfg.dw, 0, 0, False, True, src_xf=gmod)
                 gx = torch.empty_like(x)
                 L.call("msmc_reflect_pad_fold", L.ptr(gpad), L.ptr(gx), B, Hs, Ws, Cs, cfg.ph, cfg.pw)
                 if cfg.pre_slope is not None:
@@ -221,6 +247,14 @@ class _ConvFn(torch.autograd.Function):
                                  cfg.KW, 1, 1, cfg.dh, cfg.dw, cfg.dh * (cfg.KH - 1) - cfg.ph,
                                  cfg.dw * (cfg.KW - 1) - cfg.pw, False, False, src_xf=gmod, dst_xf=dmod, w_role=1,
                                  w_dims=(Cs_op, cfg.Cd))
+                elif (cfg.wstr == (cfg.KW * Cs_op * cfg.Cd, Cs_op * cfg.Cd, cfg.Cd, 1)
+                      and _umma_ok(gy_r, ld_gy, w, (Cs_op, cfg.Cd), cfg.KH, cfg.KW, cfg.Cd, Cs_op,
+                                   gx.shape[0] * gx.shape[1] * gx.shape[2], aux_r, ld_aux)):
+                    # strided conv (-> conv-transpose form) or conv-transpose op (-> forward form): same weight
+                    # with channels swapped and taps in place (image role 2)
+                    _launch_conv(gy, w, (s_kh, s_kw, s_cd, s_cs), None, None, gx, cfg.KH, cfg.KW, cfg.sh, cfg.sw,
+                                 cfg.dh, cfg.dw, cfg.ph, cfg.pw, False, not cfg.transposed, src_xf=gmod,
+                                 dst_xf=dmod, w_role=2, w_dims=(Cs_op, cfg.Cd))
                 else:
                     _launch_conv(gy, w, (s_kh, s_kw, s_cd, s_cs), None, None, gx, cfg.KH, cfg.KW, cfg.sh, cfg.sw,
                                  cfg.dh, cfg.dw, cfg.ph, cfg.pw, False, not cfg.transposed, src_xf=gmod,
@@ -292,6 +326,43 @@ def linear_cl(x, weight, bias=None, residual=None, post="none", pre_slope=None):
     return y.reshape(*lead, Co)
 
 
+# ------------------------------------------------------------------------------------------------- STFT
+class _StftFn(torch.autograd.Function):
+    """reflect-padded, windowed DFT of a waveform as a strided conv with a fixed basis; the backward is a dense
+    GEMM (spectrum gradient x basis^T -> per-frame time gradients, tensor-core eligible because the spectrum
+    channels are padded to a multiple of 32) followed by overlap-add + reflect fold, instead of a 1-output-channel
+    conv-transpose over hop phases."""
+
+    @staticmethod
+    def forward(ctx, x, basis, basis_t, hop, pad):
+        B, Ln = x.shape
+        win, F2 = basis.shape
+        frames = (Ln + 2 * pad - win) // hop + 1
+        y = torch.empty((B, 1, frames, F2), dtype=torch.float32, device=x.device)
+        _launch_conv(x.reshape(B, 1, Ln, 1), basis, (0, F2, F2, 1), None, None, y, 1, win, 1, hop, 1, 1, 0, pad,
+                     True, False)
+        ctx.save_for_backward(basis_t)
+        ctx.dims = (B, Ln, win, F2, frames, hop, pad)
+        return y.reshape(B, frames, F2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (basis_t,) = ctx.saved_tensors          # (F2, win): GEMM layout [1][Cs = F2][Cd = win]
+        B, Ln, win, F2, frames, hop, pad = ctx.dims
+        gy = gy.contiguous()
+        gframes = torch.empty((B * frames, 1, 1, win), dtype=torch.float32, device=gy.device)
+        _launch_conv(gy.reshape(B * frames, 1, 1, F2), basis_t, (F2 * win, F2 * win, win, 1), None, None, gframes,
+                     1, 1, 1, 1, 1, 1, 0, 0, False, False)
+        gx = torch.empty((B, Ln), dtype=torch.float32, device=gy.device)
+        L.call("msmc_overlap_add_fold", L.ptr(gframes), L.ptr(gx), B, frames, win, hop, Ln, pad)
+        return gx, None, None, None, None
+
+
+def stft_frames(x, basis, basis_t, hop, pad):
+    """x (B, L), basis (win, 2Fp) = hann * [cos | 0 | -sin | 0], basis_t its transpose -> (B, frames, 2Fp)"""
+    return _StftFn.apply(x, basis, basis_t, int(hop), int(pad))
+
+
 # ------------------------------------------------------------------------------------------ weight prep
 class _PrepWeightFn(torch.autograd.Function):
     """(v[, g]) -> GEMM-layout weight; weight_norm (dim=0) when g is given."""
@@ -302,8 +373,10 @@ class _PrepWeightFn(torch.autograd.Function):
         w = torch.empty(out_shape, dtype=torch.float32, device=v.device)
         inv = torch.empty(O, dtype=torch.float32, device=v.device) if g is not None else None
         L.require_cuda(v, g)
+        meta = {"flops": 0.0, "bytes": 8.0 * O * I * J, "shape": "O%d I%d J%d %s" % (O, I, J, "wn" if g is not None else "relayout")} \
+            if L._profile is not None else None
         L.call("msmc_weight_norm_fwd", L.ptr(v), L.ptr(g), L.ptr(w), L.ptr(inv), O, I, J,
-               C.c_int64(so), C.c_int64(si), C.c_int64(sj))
+               C.c_int64(so), C.c_int64(si), C.c_int64(sj), meta=meta)
         ctx.dims = (O, I, J, so, si, sj)
         ctx.has_g = g is not None
         ctx.save_for_backward(v, g, inv)
@@ -316,8 +389,10 @@ class _PrepWeightFn(torch.autograd.Function):
         gw = gw.contiguous()
         dv = torch.empty_like(v)
         dg = torch.empty(O, dtype=torch.float32, device=v.device) if ctx.has_g else None
+        meta = {"flops": 0.0, "bytes": 8.0 * O * I * J, "shape": "O%d I%d J%d %s" % (O, I, J, "wn" if ctx.has_g else "relayout")} \
+            if L._profile is not None else None
         L.call("msmc_weight_norm_bwd", L.ptr(gw), C.c_int64(so), C.c_int64(si), C.c_int64(sj), L.ptr(v), L.ptr(g),
-               L.ptr(inv), L.ptr(dv), L.ptr(dg), O, I, J)
+               L.ptr(inv), L.ptr(dv), L.ptr(dg), O, I, J, meta=meta)
         if ctx.has_g:
             dg = dg.reshape(g.shape)
         return dv, dg, None, None, None, None, None, None, None
@@ -534,33 +609,34 @@ def add_layernorm(a, r, gamma, beta, lengths=None, eps=1e-5, drop_p=0.0):
 # --------------------------------------------------------------------------------------------- pointwise
 class _SpecMagFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, spec, floor_, floor_add):
+    def forward(ctx, spec, n_freq, floor_, floor_add):
         spec = spec.contiguous()
-        F2 = spec.shape[-1]
-        F = F2 // 2
-        rows = spec.numel() // F2
-        mag = torch.empty(spec.shape[:-1] + (F,), dtype=torch.float32, device=spec.device)
+        Fp = spec.shape[-1] // 2
+        rows = spec.numel() // (2 * Fp)
+        mag = torch.empty(spec.shape[:-1] + (n_freq,), dtype=torch.float32, device=spec.device)
         L.require_cuda(spec)
-        L.call("msmc_spec_magnitude_fwd", L.ptr(spec), L.ptr(mag), C.c_int64(rows), F, C.c_float(floor_),
+        L.call("msmc_spec_magnitude_fwd", L.ptr(spec), L.ptr(mag), C.c_int64(rows), n_freq, Fp, C.c_float(floor_),
                int(floor_add))
         ctx.save_for_backward(spec, mag)
-        ctx.args = (rows, F, floor_, floor_add)
+        ctx.args = (rows, n_freq, Fp, floor_, floor_add)
         return mag
 
     @staticmethod
     def backward(ctx, gmag):
         spec, mag = ctx.saved_tensors
-        rows, F, floor_, floor_add = ctx.args
+        rows, n_freq, Fp, floor_, floor_add = ctx.args
         gmag = gmag.contiguous()
         gspec = torch.empty_like(spec)
-        L.call("msmc_spec_magnitude_bwd", L.ptr(gmag), L.ptr(spec), L.ptr(mag), L.ptr(gspec), C.c_int64(rows), F,
-               C.c_float(floor_), int(floor_add))
-        return gspec, None, None
+        L.call("msmc_spec_magnitude_bwd", L.ptr(gmag), L.ptr(spec), L.ptr(mag), L.ptr(gspec), C.c_int64(rows),
+               n_freq, Fp, C.c_float(floor_), int(floor_add))
+        return gspec, None, None, None
 
 
-def spec_magnitude(spec, floor_, floor_add=False):
-    """spec (..., 2F) = [re | im] -> (..., F)"""
-    return _SpecMagFn.apply(spec, float(floor_), bool(floor_add))
+def spec_magnitude(spec, floor_, floor_add=False, n_freq=None):
+    """spec (..., 2*Fp) = [re | pad | im | pad] -> (..., n_freq); n_freq defaults to Fp (no padding)"""
+    if n_freq is None:
+        n_freq = spec.shape[-1] // 2
+    return _SpecMagFn.apply(spec, int(n_freq), float(floor_), bool(floor_add))
 
 
 class _MelDoubleFn(torch.autograd.Function):

@@ -102,14 +102,15 @@ class WNConv2d(nn.Module):
 
     def forward(self, x, pre_slope=None, post="none"):
         KH, KW = self.kernel_size
-        Ci, Co = self.in_channels, self.out_channels
-        w = Fn.prep_conv_weight(self.weight_v, self.weight_g)       # [kh][kw][ci][co], reference tap order
         if not self.swap_hw:
+            w = Fn.prep_conv_weight(self.weight_v, self.weight_g)   # [kh][kw][ci][co]
             return Fn.conv_cl(x, w, self.bias, kernel=(KH, KW), stride=self.stride, padding=self.padding,
                               reflect=self.reflect, pre_slope=pre_slope, post=post)
+        # exchanged spatial axes: transpose the taps, then the standard contiguous GEMM layout [kw][kh][ci][co]
+        # (the weight norm runs over (ci, kh, kw), so it is unaffected by the permutation)
+        w = Fn.prep_conv_weight(self.weight_v.transpose(2, 3), self.weight_g)
         return Fn.conv_cl(x, w, self.bias, kernel=(KW, KH), stride=self.stride[::-1], padding=self.padding[::-1],
-                          reflect=self.reflect, pre_slope=pre_slope, post=post,
-                          wstr=(Ci * Co, KW * Ci * Co, Co, 1), out_channels=Co)
+                          reflect=self.reflect, pre_slope=pre_slope, post=post)
 
 
 class LayerNormParams(nn.LayerNorm):

@@ -41,10 +41,12 @@ SIGNATURES = {
     "msmc_conv_forward": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _P]),
     "msmc_conv_wgrad_workspace": (C.c_int64, [_G]),
     "msmc_conv_wgrad": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _I64, _P]),
-    "msmc_umma_tile_n": (C.c_int, [_I32]),
-    "msmc_weight_image_elems": (C.c_int64, [_I32, _I32, _I32, _I32, _I32]),
-    "msmc_weight_image": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
-    "msmc_conv_forward_umma": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _I32, _P]),
+    "msmc_umma_tile_n": (C.c_int, [_I32, _I64]),
+    "msmc_weight_image_elems": (C.c_int64, [_I32, _I32, _I32, _I32, _I32, _I32]),
+    "msmc_weight_image": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "msmc_conv_forward_umma": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P]),
+    "msmc_conv_wgrad_umma_workspace": (C.c_int64, [_G]),
+    "msmc_conv_wgrad_umma": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "msmc_weight_norm_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I64, _I64, _I64, _P]),
     "msmc_weight_norm_bwd": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
     "msmc_reflect_pad_fold": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
@@ -57,12 +59,13 @@ SIGNATURES = {
     "msmc_add_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _F, _P, _U64, _P]),
     "msmc_add_layernorm_bwd_workspace": (C.c_int64, [_I32]),
     "msmc_add_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _U64, _P]),
-    "msmc_spec_magnitude_fwd": (C.c_int, [_P, _P, _I64, _I32, _F, _I32, _P]),
-    "msmc_spec_magnitude_bwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _F, _I32, _P]),
+    "msmc_spec_magnitude_fwd": (C.c_int, [_P, _P, _I64, _I32, _I32, _F, _I32, _P]),
+    "msmc_spec_magnitude_bwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _I32, _P]),
     "msmc_mel_double_fwd": (C.c_int, [_P, _P, _I64, _F, _F, _P]),
     "msmc_mel_double_bwd": (C.c_int, [_P, _P, _P, _I64, _F, _F, _P]),
     "msmc_log_clamp_fwd": (C.c_int, [_P, _P, _I64, _F, _P]),
     "msmc_log_clamp_bwd": (C.c_int, [_P, _P, _P, _I64, _F, _P]),
+    "msmc_overlap_add_fold": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "msmc_gated_act_fwd": (C.c_int, [_P, _P, _I64, _I32, _P]),
     "msmc_gated_act_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P]),
     "msmc_version": (C.c_int, []),
@@ -72,7 +75,7 @@ SIGNATURES = {
 _STATUS = {1: "MSMC_ERR_BAD_ARG", 2: "MSMC_ERR_LAUNCH", 3: "MSMC_ERR_UNSUPPORTED"}
 _lib = None
 # kernels each entry point launches (bench.py's `gpu_launches` is the sum over the timed region)
-KERNELS_PER_CALL = {"msmc_conv_wgrad": 2, "msmc_vq_ema_update": 2, "msmc_attention_bwd": 2,
+KERNELS_PER_CALL = {"msmc_conv_wgrad": 2, "msmc_conv_wgrad_umma": 2, "msmc_vq_ema_update": 2, "msmc_attention_bwd": 2,
                     "msmc_add_layernorm_bwd": 2}
 launch_count = 0   # kernels launched through the C-ABI so far
 _profile = None    # when a list: (name, meta, start_event, end_event) per call, for bench.py's roofline pass

@@ -42,8 +42,9 @@ class MelLoss(nn.Module):
         self.fft_size, self.hop_size, self.win_size = fft_size, hop_size, win_size
         self.sample_rate, self.num_mels = sample_rate, num_mels
         self.n_freq = fft_size // 2 + 1
-        basis, self.left = dft_basis(fft_size, win_size, normalized=False)
+        basis, self.left, self.n_freq_pad = dft_basis(fft_size, win_size, normalized=False)
         self.register_buffer("basis", basis, persistent=False)
+        self.register_buffer("basis_t", basis.t().contiguous(), persistent=False)
         self.register_buffer("mel_basis", mel_filterbank_slaney(sample_rate, fft_size, num_mels, 0,
                                                                 sample_rate // 2), persistent=False)
 
@@ -51,10 +52,8 @@ class MelLoss(nn.Module):
         """y (B, L) -> log-mel (B, frames, num_mels)"""
         B, L = y.shape
         pad = int((self.fft_size - self.hop_size) / 2) - self.left
-        spec = Fn.conv_cl(y.reshape(B, 1, L, 1), self.basis, kernel=(1, self.win_size), stride=(1, self.hop_size),
-                          padding=(0, pad), reflect=True, wstr=(0, 2 * self.n_freq, 2 * self.n_freq, 1),
-                          out_channels=2 * self.n_freq).squeeze(1)
-        mag = Fn.spec_magnitude(spec, 1e-9, True)
+        spec = Fn.stft_frames(y, self.basis, self.basis_t, self.hop_size, pad)
+        mag = Fn.spec_magnitude(spec, 1e-9, True, self.n_freq)
         mel = Fn.linear_cl(mag, self.mel_basis)
         return Fn.log_clamp(mel, 1e-5)
 

@@ -14,10 +14,10 @@ class ExponentialDecayLRScheduler(object):
                 lr = base * self.decay_learning_rate ** ((iteration - self.warmup_steps) / self.decay_scale)
             lr = max(lr, self.final_learning_rate)
             for group in opt.param_groups:
-                if isinstance(group["lr"], float) or not hasattr(group["lr"], "fill_"):
-                    group["lr"] = lr
+                if hasattr(group["lr"], "fill_"):
+                    group["lr"].fill_(lr)       # device tensor (capturable optimizers): no re-capture needed
                 else:
-                    group["lr"].fill_(lr)
+                    group["lr"] = lr
 
 
 def build_lr_scheduler(config):

@@ -62,8 +62,12 @@ class QuantizerLoss(nn.Module):
 class VQGANTrainer(BaseTrainer):
     def __init__(self, config, model, num_gpus=1, rank=0, warmup_steps=0, lambda_frame=1.0,
                  eval_inteval_iters=1000, grad_clip_thresh=1.0, sample_lengths=24000, lambda_vq=1, lambda_pr=1,
-                 lambda_fm=2, lambda_stft=45, stft_loss_func="mel_loss", stft_loss_config=None):
+                 lambda_fm=2, lambda_stft=45, stft_loss_func="mel_loss", stft_loss_config=None, cuda_graph=False):
         super().__init__(config, model, num_gpus, rank)
+        # cuda_graph=True: the sync-free step body is captured once per (shape, phase) into a CUDA graph and
+        # replayed -- ~2.6k kernel launches and all Python/autograd dispatch collapse into one graph launch
+        self.use_cuda_graph = bool(cuda_graph)
+        self._graphs = {}
         self.lambda_frame, self.warmup_steps = lambda_frame, warmup_steps
         self.frameshift = self.config.dataset.frameshift[self.config.dataset.feature.index("mel")]
         self.frame_lengths = -1 if sample_lengths == -1 else sample_lengths // self.frameshift
@@ -103,17 +107,51 @@ class VQGANTrainer(BaseTrainer):
     def train_step(self, batch, iteration, frame_windows=None):
         mel, mel_length = batch["mel"], batch["mel_length"]
         wav = batch["wav"]
+        step = self._graphed_step if (self.use_cuda_graph and mel.is_cuda) else self._step
         if iteration < self.warmup_steps:
-            return self._step(mel, mel_length, None, None, warmup=True, gan=False)
+            return step(mel, mel_length, None, None, warmup=True, gan=False)
         if frame_windows is None:
             frame_windows, _ = self.random_select(mel_length.cpu())
-        starts = torch.as_tensor([w[0] for w in frame_windows], device=mel.device, dtype=torch.int64)
-        return self._step(mel, mel_length, wav, starts, warmup=False, gan=iteration > self.warmup_steps)
+        starts = torch.as_tensor([w[0] for w in frame_windows], dtype=torch.int64)
+        if mel.is_cuda:
+            starts = starts.pin_memory().to(mel.device, non_blocking=True)
+        return step(mel, mel_length, wav, starts, warmup=False, gan=iteration > self.warmup_steps)
+
+    def _graphed_step(self, mel, mel_length, wav, starts, warmup, gan):
+        """CUDA-graph replay of `_step` on static input buffers (one graph per input shape and phase)."""
+        key = (tuple(mel.shape), None if wav is None else tuple(wav.shape), warmup, gan)
+        st = self._graphs.get(key)
+        if st is None:
+            st = {"n": 0, "inp": [None if t is None else torch.empty_like(t) for t in (mel, mel_length, wav, starts)]}
+            self._graphs[key] = st
+        for dst, src in zip(st["inp"], (mel, mel_length, wav, starts)):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        if st["n"] < 3:
+            # eager warm-up on a side stream (initialises optimizer state, weight-norm caches, autotuned attributes)
+            st["n"] += 1
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                out = self._step(*st["inp"], warmup=warmup, gan=gan)
+            torch.cuda.current_stream().wait_stream(side)
+            return out
+        if "graph" not in st:
+            self.optimizer.zero_grad()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["out"] = self._step(*st["inp"], warmup=warmup, gan=gan)
+            st["graph"] = graph
+        st["graph"].replay()
+        return st["out"]
 
     def _step(self, mel, mel_length, wav, starts, warmup, gan):
         """sync-free body; everything inside is device work (graph-capturable)"""
         losses = {}
         ae, disc = self.model.autoencoder, getattr(self.model, "discriminator", None)
+        if mel.is_cuda:
+            from msmctts._b200.functional import DeviceRng
+            DeviceRng.advance(mel.device)      # device-side seed bump: a graph replay draws fresh dropout masks
         if warmup:
             output = ae(mel, mel_length, warmup=True)
         else:

@@ -12,6 +12,8 @@ def get_optimizer(parameters, config):
     kw = dict(lr=config.learning_rate, betas=tuple(config.betas), eps=config.eps, weight_decay=config.weight_decay)
     if parameters and parameters[0].is_cuda:
         kw["capturable"] = True
+        # device-resident learning rate: the scheduler can change it between CUDA-graph replays
+        kw["lr"] = torch.tensor(float(config.learning_rate), dtype=torch.float32, device=parameters[0].device)
     if name == "Adam":
         return Adam(parameters, **kw)
     if name == "AdamW":

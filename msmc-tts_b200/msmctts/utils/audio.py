@@ -31,16 +31,22 @@ def create_fb_matrix(n_freqs, f_min, f_max, n_mels, sample_rate, norm=None):
 
 
 def dft_basis(n_fft, win_length, normalized, dtype=torch.float32):
-    """(win_length, 2F) basis [cos | -sin] * hann(win_length), for the window's non-zero span only.
-    torch.stft centres a short window inside n_fft (left pad (n_fft - win)/2); returns (basis, left)."""
+    """(win_length, 2*Fp) basis [cos | 0 | -sin | 0] * hann(win_length), for the window's non-zero span only; each
+    half is zero-padded from F = n_fft/2+1 to Fp = a multiple of 16 so the spectrum has 32k channels (tensor-core
+    GEMM eligibility).  torch.stft centres a short window inside n_fft (left pad (n_fft - win)/2).
+    Returns (basis, left, Fp)."""
     left = (n_fft - win_length) // 2
+    F = n_fft // 2 + 1
+    Fp = (F + 15) // 16 * 16
     k = np.arange(win_length, dtype=np.float64) + left
-    f = np.arange(n_fft // 2 + 1, dtype=np.float64)
+    f = np.arange(F, dtype=np.float64)
     ang = 2.0 * np.pi * np.outer(k, f) / n_fft
     win = torch.hann_window(win_length, dtype=torch.float64).numpy()     # periodic, like the reference
     scale = (1.0 / math.sqrt(n_fft)) if normalized else 1.0
-    basis = np.concatenate([np.cos(ang), -np.sin(ang)], axis=1) * win[:, None] * scale
-    return torch.from_numpy(basis).to(dtype), left
+    basis = np.zeros((win_length, 2 * Fp))
+    basis[:, :F] = np.cos(ang) * win[:, None] * scale
+    basis[:, Fp:Fp + F] = -np.sin(ang) * win[:, None] * scale
+    return torch.from_numpy(basis).to(dtype), left, Fp
 
 
 class MelScale(nn.Module):
@@ -68,23 +74,21 @@ class TorchSTFT(nn.Module):
         self.ref_level_db, self.min_level_db = ref_level_db, min_level_db
         self.normalized, self.domain = normalized, domain
         self.n_freq = fft_size // 2 + 1
-        basis, self.left = dft_basis(fft_size, win_size, normalized)
-        self.register_buffer("basis", basis, persistent=False)          # (win, 2F): GEMM layout [tap][1][2F]
+        basis, self.left, self.n_freq_pad = dft_basis(fft_size, win_size, normalized)
+        self.register_buffer("basis", basis, persistent=False)          # (win, 2Fp): GEMM layout [tap][1][2Fp]
+        self.register_buffer("basis_t", basis.t().contiguous(), persistent=False)
         self.mel_scale = MelScale(self.n_freq, sample_rate, n_stft=self.n_freq) if mel_scale else None
 
     def spectrum_cl(self, x, center=True, pad=None):
-        """x (B, L) -> (B, frames, 2F) = [re | im]"""
+        """x (B, L) -> (B, frames, 2Fp) = [re | pad | im | pad]"""
         B, L = x.shape
         p = (self.fft_size // 2 if center else 0) if pad is None else pad
         p = p - self.left
-        y = Fn.conv_cl(x.reshape(B, 1, L, 1), self.basis, kernel=(1, self.win_size), stride=(1, self.hop_size),
-                       padding=(0, p), reflect=True, wstr=(0, 2 * self.n_freq, 2 * self.n_freq, 1),
-                       out_channels=2 * self.n_freq)
-        return y.squeeze(1)
+        return Fn.stft_frames(x, self.basis, self.basis_t, self.hop_size, p)
 
     def transform_cl(self, x):
         """x (B, L) -> (B, frames, F, C) with C = 2 ('double': lin, log), else 1"""
-        mag = Fn.spec_magnitude(self.spectrum_cl(x), 1e-7, False)
+        mag = Fn.spec_magnitude(self.spectrum_cl(x), 1e-7, False, self.n_freq)
         if self.mel_scale is not None:
             mag = self.mel_scale.forward_cl(mag)
         if self.domain == "double":
