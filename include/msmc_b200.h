@@ -87,6 +87,13 @@ int msmc_conv_forward_umma(const msmc_conv_geom* g, const float* src, const floa
                            const float* bias, const float* residual, const float* dst_aux, float* dst,
                            int32_t split, int32_t BN, void* stream);
 
+/* stride-1 convolutions whose taps are constant row shifts in flattened pixel space (1-D convs, (k,1) convs) reuse ONE
+ * staged operand tile for all taps (shifted shared-memory descriptors); same contract as msmc_conv_forward_umma */
+int msmc_conv_reuse_eligible(const msmc_conv_geom* g);
+int msmc_conv_forward_umma_reuse(const msmc_conv_geom* g, const float* src, const float* src_aux,
+                                 const float* wimg, const float* bias, const float* residual,
+                                 const float* dst_aux, float* dst, int32_t split, int32_t BN, void* stream);
+
 /* tensor-core weight gradient (Cs % 32 == 0): both operands are consumed MN-major straight from the channels-last
  * activations; same contract and workspace layout as msmc_conv_wgrad */
 int64_t msmc_conv_wgrad_umma_workspace(const msmc_conv_geom* g);

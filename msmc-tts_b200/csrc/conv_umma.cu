@@ -21,6 +21,7 @@
 // limiter.  SPLIT = false is plain TF32 (what the reference's cuDNN convolutions do on Ampere+ by default).
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace msmc {
 namespace {
@@ -59,6 +60,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// producer-side "stage is full" signal: every thread publishes its shared-memory writes to the async proxy, the
+// warp converges, and ONE lane arrives (256 per-thread arrivals on one mbarrier serialise for ~1k cycles)
+__device__ __forceinline__ void publish_and_arrive_warp(uint64_t* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -102,6 +110,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// unsigned division by a runtime constant for dividends < 2^31: q = (umulhi(n, mul) + n) >> shr
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+__host__ inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.shr = l;
+  f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return (__umulhi(n, f.mul) + n) >> f.shr; }
 
 struct UmmaArgs {
   msmc_conv_geom g;
@@ -216,7 +239,7 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_umma_kernel(const UmmaArg
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], UMF_PRODUCERS + 1);   // producer arrivals + 1 arrive.expect_tx for the weight tile
+      mbar_init(&full_bar[s], UMF_PRODUCERS / 32 + 1);   // one arrival per producer warp + 1 arrive.expect_tx (weights)
       mbar_init(&empty_bar[s], 1);                  // one tcgen05.commit
     }
     mbar_init(accum_bar, 1);
@@ -258,12 +281,12 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_umma_kernel(const UmmaArg
     }
     constexpr bool NEED_AUX = (XFC == XFC_GENERIC);
     const bool need_aux = NEED_AUX && xf_needs_aux(g.src_xf);
-    float4 v[4], u[4];
+    float4 v0[4], u0[4], v1[4], u1[4];          // two stages of loads in flight (prefetch distance 2)
     int kc_n = 0, kh_n = 0, kw_n = 0, ti_n = 0;   // (chunk, tap) of the NEXT stage to gather
     if (TRANSPOSED && T > 0) { kh_n = s_tap_kh[0]; kw_n = s_tap_kw[0]; }
 
-    // raw global loads only (no dependent math), so they stay in flight across the barrier round-trip
-    auto gather = [&]() {
+    // raw global loads only (no dependent math), so they stay in flight across the barrier round-trips
+    auto gather = [&](float4 (&v)[4], float4 (&u)[4]) {
       const int coff = kc_n * UM_BK + chunk * 4;
       const int dh = kh_n * g.dh, dw = kw_n * g.dw;
 #pragma unroll
@@ -306,11 +329,10 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_umma_kernel(const UmmaArg
       }
     };
 
-    gather();
     int s = 0;
     uint32_t ph = 0;
     const uint32_t dst_off = (uint32_t)(rsub >> 3) * 1024u + (uint32_t)r8 * 128u + (uint32_t)((chunk ^ r8) << 4);
-    for (int ks = 0; ks < n_k; ++ks) {
+    auto produce = [&](int ks, float4 (&v)[4], float4 (&u)[4]) {
       mbar_wait(&empty_bar[s], ph ^ 1u);
       if (tid == 0) {
         mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
@@ -335,10 +357,16 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_umma_kernel(const UmmaArg
           *reinterpret_cast<float4*>(d) = x;
         }
       }
-      if (ks + 1 < n_k) gather();   // issue the next stage's loads before signalling this one
-      fence_proxy_async();
-      mbar_arrive(&full_bar[s]);
+      if (ks + 2 < n_k) gather(v, u);   // refill this register set with the loads of stage ks + 2
+      publish_and_arrive_warp(&full_bar[s]);
       if (++s == STAGES) { s = 0; ph ^= 1u; }
+    };
+
+    if (n_k > 0) gather(v0, u0);
+    if (n_k > 1) gather(v1, u1);
+    for (int ks = 0; ks < n_k; ks += 2) {
+      produce(ks, v0, u0);
+      if (ks + 1 < n_k) produce(ks + 1, v1, u1);
     }
 
     // ================================= epilogue =================================
@@ -380,6 +408,29 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_umma_kernel(const UmmaArg
       float acc[16];
       tmem_ld16(taddr + (uint32_t)c0, acc);
       if (row_ok) {
+        const bool full16 = n0 + c0 + 16 <= g.Cd;
+        if (full16 && !dneed_aux && (g.ld_dst & 3) == 0 && (!a.residual || (g.ld_res & 3) == 0)) {
+          // fast path: 16 full columns, vector loads of bias / residual, vector stores
+          float* out = a.dst + m * g.ld_dst + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 x = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            if (a.bias) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0 + j));
+              x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+            }
+            if (g.dst_xf != MSMC_XF_NONE) {
+              x.x = apply_xf(g.dst_xf, g.dst_slope, x.x, 0.f); x.y = apply_xf(g.dst_xf, g.dst_slope, x.y, 0.f);
+              x.z = apply_xf(g.dst_xf, g.dst_slope, x.z, 0.f); x.w = apply_xf(g.dst_xf, g.dst_slope, x.w, 0.f);
+            }
+            if (a.residual) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(a.residual + m * g.ld_res + n0 + c0 + j));
+              x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
+            }
+            *reinterpret_cast<float4*>(out + j) = x;
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int n = n0 + c0 + j;
@@ -395,7 +446,7 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_umma_kernel(const UmmaArg
           }
         }
         float* out = a.dst + m * g.ld_dst + n0 + c0;
-        if (n0 + c0 + 16 <= g.Cd && (g.ld_dst & 3) == 0) {
+        if (full16 && (g.ld_dst & 3) == 0) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<float4*>(out + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
@@ -450,6 +501,272 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_umma_kernel(const UmmaArg
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Stride-1 convolution with TAP REUSE.  For a stride-1 conv every tap reads the same source rows shifted by a
+// constant number of pixels, so the operand tile of one 32-channel chunk is staged ONCE (128 + max-shift rows,
+// transformed / split in registers as before) and each tap's tcgen05.mma simply starts its shared-memory
+// descriptor `shift` rows further down: start address += shift * 128 B with the descriptor's matrix-base-offset
+// field = (shift & 7), which tells the tensor core where in the 8-row SWIZZLE_128B pattern the tile begins.
+// Producer work drops by the number of taps (3..11x on the MRF / FFN / MPD convs) and the kernel becomes
+// MMA / HBM bound instead of producer bound.  A dedicated warp streams the weight tiles (cp.async.bulk) through
+// their own ring, decoupled from the operand ring.
+//   applies to: forward form, stride 1, zero padding, 1-D tap pattern in flattened pixel space
+//               (Hs == 1, or KW == 1 with pw == 0), max shift <= 64 rows.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int RU_ROWS = 192;                  // 128 output rows + up to 64 rows of tap reach
+constexpr int RU_PRODUCERS = 256;
+constexpr int RU_THREADS = RU_PRODUCERS + 64;  // + MMA warp + weight-loader warp
+
+struct ReuseArgs {
+  msmc_conv_geom g;
+  const float* src;
+  const float* src_aux;
+  const float* wimg;
+  const float* bias;
+  const float* residual;
+  const float* dst_aux;
+  float* dst;
+  int Ls, Ld;            // pixels per batch element (source / destination)
+  int pad_rows;          // ph * Ws + pw
+  int tap_stride;        // rows between consecutive taps (dh * Ws or dw)
+  int n_taps;
+  int tiles_per_batch;
+  int base_off_mode;     // bring-up switch: 0 = descriptor base offset left 0, 1 = (addr >> 7) & 7
+};
+
+__device__ __forceinline__ uint64_t make_desc_off(uint32_t smem_addr, int mode) {
+  // K-major SWIZZLE_128B descriptor whose start is not 1024-byte aligned
+  uint64_t d = make_desc(smem_addr);
+  if (mode == 1) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+  return d;
+}
+
+template <int BN, bool SPLIT, int NA, int NBS, int XFC>
+__global__ void __launch_bounds__(RU_THREADS, 1) conv_umma_reuse_kernel(const ReuseArgs a) {
+  const msmc_conv_geom& g = a.g;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NP = SPLIT ? 2 : 1;
+  constexpr int A_PLANE = RU_ROWS * 128;        // 24 KB
+  constexpr int B_PLANE = BN * 128;
+  constexpr int A_BYTES = NP * A_PLANE;
+  constexpr int B_BYTES = NP * B_PLANE;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + NA * A_BYTES;
+  uint64_t* fa = reinterpret_cast<uint64_t*>(sB + NBS * B_BYTES);
+  uint64_t* ea = fa + NA;
+  uint64_t* fb = ea + NA;
+  uint64_t* eb = fb + NBS;
+  uint64_t* accum_bar = eb + NBS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.x / a.tiles_per_batch;
+  const int l0 = (blockIdx.x - b * a.tiles_per_batch) * UM_BM;
+  const int n_tile = blockIdx.y, n_tiles = gridDim.y;
+  const int KC = g.Cs / UM_BK;
+  const int T = a.n_taps;
+  const int r_in = UM_BM + (T - 1) * a.tap_stride;      // rows staged per chunk (<= RU_ROWS)
+  constexpr int MMA_WARP = RU_PRODUCERS / 32, LOAD_WARP = MMA_WARP + 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(&fa[i], RU_PRODUCERS / 32); mbar_init(&ea[i], 1); }
+    for (int i = 0; i < NBS; ++i) { mbar_init(&fb[i], 1); mbar_init(&eb[i], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < MMA_WARP) {
+    // ================================= operand producers =================================
+    const int chunk = tid & 7;
+    const int rsub = tid >> 3;                 // 0..31; rows rsub + 32*i, i = 0..5
+    const int r8 = rsub & 7;
+    constexpr bool NEED_AUX = (XFC == XFC_GENERIC);
+    const bool need_aux = NEED_AUX && xf_needs_aux(g.src_xf);
+    const int64_t pix0 = (int64_t)b * a.Ls;
+    float4 v[6], u[6];
+    auto gather = [&](int kc) {
+      const int coff = kc * UM_BK + chunk * 4;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int r = rsub + 32 * i;
+        const int p = l0 - a.pad_rows + r;               // source pixel inside this batch element
+        if (r < r_in && (unsigned)p < (unsigned)a.Ls) {
+          v[i] = __ldg(reinterpret_cast<const float4*>(a.src + (pix0 + p) * g.ld_src + coff));
+          if (NEED_AUX && need_aux)
+            u[i] = __ldg(reinterpret_cast<const float4*>(a.src_aux + (pix0 + p) * g.ld_saux + coff));
+        } else {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (NEED_AUX) u[i] = v[i];
+        }
+      }
+    };
+    gather(0);
+    int sa = 0;
+    uint32_t pa = 0;
+    const uint32_t dst_off = (uint32_t)(rsub >> 3) * 1024u + (uint32_t)r8 * 128u + (uint32_t)((chunk ^ r8) << 4);
+    for (int kc = 0; kc < KC; ++kc) {
+      mbar_wait(&ea[sa], pa ^ 1u);
+      uint8_t* dstbase = sA + sa * A_BYTES + dst_off;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if (rsub + 32 * i < r_in) {
+          const float4 x = xf4<XFC>(g, v[i], NEED_AUX ? u[i] : make_float4(0.f, 0.f, 0.f, 0.f));
+          uint8_t* d = dstbase + i * 4096;
+          if (SPLIT) {
+            const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+            *reinterpret_cast<float4*>(d) = hi;
+            *reinterpret_cast<float4*>(d + A_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+          } else {
+            *reinterpret_cast<float4*>(d) = x;
+          }
+        }
+      }
+      if (kc + 1 < KC) gather(kc + 1);
+      publish_and_arrive_warp(&fa[sa]);
+      if (++sa == NA) { sa = 0; pa ^= 1u; }
+    }
+
+    // ================================= epilogue =================================
+    const int lane_grp = warp & 3;
+    const int l = l0 + lane_grp * 32 + (tid & 31);
+    const bool row_ok = l < a.Ld;
+    const int64_t m = (int64_t)b * a.Ld + l;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+    const int n0 = n_tile * BN;
+    const bool dneed_aux = xf_needs_aux(g.dst_xf);
+    constexpr int CHALF = BN / 2;
+    const int cbeg = (warp >> 2) * CHALF;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + CHALF; c0 += 16) {
+      float acc[16];
+      tmem_ld16(taddr + (uint32_t)c0, acc);
+      if (row_ok) {
+        const bool full16 = n0 + c0 + 16 <= g.Cd;
+        if (full16 && !dneed_aux && (g.ld_dst & 3) == 0 && (!a.residual || (g.ld_res & 3) == 0)) {
+          // fast path: 16 full columns, vector loads of bias / residual, vector stores
+          float* out = a.dst + m * g.ld_dst + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 x = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            if (a.bias) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0 + j));
+              x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+            }
+            if (g.dst_xf != MSMC_XF_NONE) {
+              x.x = apply_xf(g.dst_xf, g.dst_slope, x.x, 0.f); x.y = apply_xf(g.dst_xf, g.dst_slope, x.y, 0.f);
+              x.z = apply_xf(g.dst_xf, g.dst_slope, x.z, 0.f); x.w = apply_xf(g.dst_xf, g.dst_slope, x.w, 0.f);
+            }
+            if (a.residual) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(a.residual + m * g.ld_res + n0 + c0 + j));
+              x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
+            }
+            *reinterpret_cast<float4*>(out + j) = x;
+          }
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < g.Cd) {
+            float x = acc[j];
+            if (a.bias) x += __ldg(a.bias + n);
+            if (g.dst_xf != MSMC_XF_NONE) {
+              const float aux = dneed_aux ? __ldg(a.dst_aux + m * g.ld_daux + n) : 0.f;
+              x = apply_xf(g.dst_xf, g.dst_slope, x, aux);
+            }
+            if (a.residual) x += __ldg(a.residual + m * g.ld_res + n);
+            acc[j] = x;
+          }
+        }
+        float* out = a.dst + m * g.ld_dst + n0 + c0;
+        if (full16 && (g.ld_dst & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(out + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < g.Cd) out[j] = acc[j];
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == MMA_WARP) {
+    // ================================= MMA issuer =================================
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(UM_BM >> 4) << 24);
+    if ((tid & 31) == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(&fa[sa], pa);
+        const uint32_t a_base = smem_u32(sA + sa * A_BYTES);
+        for (int t = 0; t < T; ++t) {
+          mbar_wait(&fb[sb], pb);
+          tc_fence_after();
+          const uint32_t a_addr = a_base + (uint32_t)(t * a.tap_stride) * 128u;   // tap = row shift of the staged tile
+          const uint32_t b_addr = smem_u32(sB + sb * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < UM_BK / 8; ++k) {
+            const uint64_t a_hi = make_desc_off(a_addr + k * 32, a.base_off_mode), b_hi = make_desc(b_addr + k * 32);
+            const uint32_t acc = (kc > 0 || t > 0 || k > 0) ? 1u : 0u;
+            if (SPLIT) {
+              const uint64_t a_lo = make_desc_off(a_addr + A_PLANE + k * 32, a.base_off_mode),
+                             b_lo = make_desc(b_addr + B_PLANE + k * 32);
+              umma_tf32(tmem_base, a_lo, b_hi, IDESC, acc);
+              umma_tf32(tmem_base, a_hi, b_lo, IDESC, 1u);
+              umma_tf32(tmem_base, a_hi, b_hi, IDESC, 1u);
+            } else {
+              umma_tf32(tmem_base, a_hi, b_hi, IDESC, acc);
+            }
+          }
+          umma_commit(&eb[sb]);
+          if (++sb == NBS) { sb = 0; pb ^= 1u; }
+        }
+        umma_commit(&ea[sa]);
+        if (++sa == NA) { sa = 0; pa ^= 1u; }
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    // ================================= weight-tile loader =================================
+    if ((tid & 31) == 0) {
+      int sb = 0;
+      uint32_t pb = 0;
+      for (int kc = 0; kc < KC; ++kc)
+        for (int t = 0; t < T; ++t) {
+          mbar_wait(&eb[sb], pb ^ 1u);
+          mbar_arrive_expect_tx(&fb[sb], B_BYTES);
+          const float* wsrc = a.wimg + (((int64_t)t * KC + kc) * n_tiles + n_tile) * (B_BYTES / 4);
+          bulk_g2s(sB + sb * B_BYTES, wsrc, B_BYTES, &fb[sb]);
+          if (++sb == NBS) { sb = 0; pb ^= 1u; }
+        }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN)
+                 : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Weight gradient on the tensor cores:  dW[(tap, cs), cd] = sum_m  xf(src)[gather(m, tap), cs] * xf(gout)[m, cd]
 //
@@ -472,6 +789,7 @@ struct UmmaWgradArgs {
   int64_t rows_per_split;  // multiple of 32
   int want_bias;
   int gvec;                // gout rows can be read with 16-byte loads
+  FastDiv div_hw, div_w;   // m -> (b, rem) by Hd*Wd, rem -> (hd, wd) by Wd
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
@@ -523,7 +841,7 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const U
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], UMF_PRODUCERS);
+      mbar_init(&full_bar[s], UMF_PRODUCERS / 32);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
@@ -562,11 +880,11 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const U
     const bool need_aux = NEED_AUX && xf_needs_aux(g.src_xf);
     const bool do_bias = a.want_bias && blockIdx.x == 0 && !is_a && nb_ok;
     const bool active = is_a ? true : nb_ok;
-    float4 v[8], u[8];
+    float4 v0[8], u0[8], v1[8], u1[8];         // two stages of loads in flight
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
     int64_t m_next = mbeg + psub;              // position of row i = 0 of the next stage to gather
 
-    auto gather = [&]() {
+    auto gather = [&](float4 (&v)[8], float4 (&u)[8]) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int64_t m = m_next + 4 * i;
@@ -575,11 +893,13 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const U
           bool ok = m_ok && rb_ok;
           int64_t pix = 0;
           if (ok) {
-            const int b = (int)(m / ((int64_t)g.Hd * g.Wd));
-            const int rem = (int)(m % ((int64_t)g.Hd * g.Wd));
-            const int hd = rem / g.Wd, wd = rem - hd * g.Wd;
-            int hs = hd * g.sh + kh * g.dh - g.ph;
-            int ws = wd * g.sw + kw * g.dw - g.pw;
+            const uint32_t mu = (uint32_t)m;
+            const uint32_t b = fdiv(mu, a.div_hw);
+            const uint32_t rem = mu - b * a.div_hw.d;
+            const uint32_t hd = fdiv(rem, a.div_w);
+            const uint32_t wd = rem - hd * a.div_w.d;
+            int hs = (int)hd * g.sh + kh * g.dh - g.ph;
+            int ws = (int)wd * g.sw + kw * g.dw - g.pw;
             if (g.pad_reflect) { hs = reflect1(hs, g.Hs); ws = reflect1(ws, g.Ws); }
             else ok = (unsigned)hs < (unsigned)g.Hs && (unsigned)ws < (unsigned)g.Ws;
             pix = ((int64_t)b * g.Hs + hs) * g.Ws + ws;
@@ -614,10 +934,9 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const U
       m_next += 32;
     };
 
-    gather();
     int s = 0;
     uint32_t ph = 0;
-    for (int ks = 0; ks < n_k; ++ks) {
+    auto produce = [&](int ks, float4 (&v)[8], float4 (&u)[8]) {
       mbar_wait(&empty_bar[s], ph ^ 1u);
       if (active) {
         uint8_t* base = (is_a ? sA + s * A_BYTES : sB + s * B_BYTES) + (uint32_t)blk * 4096u;
@@ -650,10 +969,16 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const U
           }
         }
       }
-      if (ks + 1 < n_k) gather();
-      fence_proxy_async();
-      mbar_arrive(&full_bar[s]);
+      if (ks + 2 < n_k) gather(v, u);
+      publish_and_arrive_warp(&full_bar[s]);
       if (++s == STAGES) { s = 0; ph ^= 1u; }
+    };
+
+    gather(v0, u0);
+    if (n_k > 1) gather(v1, u1);
+    for (int ks = 0; ks < n_k; ks += 2) {
+      produce(ks, v0, u0);
+      if (ks + 1 < n_k) produce(ks + 1, v1, u1);
     }
 
     // ================================= epilogue =================================
@@ -857,16 +1182,20 @@ extern "C" int msmc_conv_forward_umma(const msmc_conv_geom* gp, const float* src
     else if (xfc == XFC_LRELU) LAUNCH_UMMA_X(BN_, SPLIT_, ST_, XFC_LRELU); \
     else LAUNCH_UMMA_X(BN_, SPLIT_, ST_, XFC_GENERIC);               \
   } while (0)
+  // short reduction loops (the M-heavy, few-channel layers) are dominated by per-CTA prologue / epilogue latency:
+  // a 2-stage ring halves the shared-memory footprint so two CTAs share an SM and overlap those phases
+  const int n_k_est = g.KH * g.KW * (g.Cs / UM_BK) / (g.transposed ? g.sh * g.sw : 1);
+  const bool shallow = n_k_est <= 24;
   if (split) {
     switch (bn) {
-      case 32: LAUNCH_UMMA(32, true, 4); break;    // 4 x 40 KB
-      case 64: LAUNCH_UMMA(64, true, 4); break;    // 4 x 48 KB
-      default: LAUNCH_UMMA(128, true, 3); break;   // 3 x 64 KB
+      case 32: if (shallow) LAUNCH_UMMA(32, true, 2); else LAUNCH_UMMA(32, true, 4); break;   // 2 or 4 x 40 KB
+      case 64: if (shallow) LAUNCH_UMMA(64, true, 2); else LAUNCH_UMMA(64, true, 4); break;   // 2 or 4 x 48 KB
+      default: LAUNCH_UMMA(128, true, 3); break;                                               // 3 x 64 KB
     }
   } else {
     switch (bn) {
-      case 32: LAUNCH_UMMA(32, false, 4); break;
-      case 64: LAUNCH_UMMA(64, false, 4); break;
+      case 32: if (shallow) LAUNCH_UMMA(32, false, 2); else LAUNCH_UMMA(32, false, 4); break;
+      case 64: if (shallow) LAUNCH_UMMA(64, false, 2); else LAUNCH_UMMA(64, false, 4); break;
       default: LAUNCH_UMMA(128, false, 4); break;
     }
   }
@@ -917,6 +1246,9 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
   a.g = g; a.src = src; a.src_aux = src_aux; a.gout = gout; a.gout_aux = gout_aux; a.partial = workspace;
   a.rows_per_split = ceil_div64(ceil_div64(M, splits), 32) * 32;
   a.want_bias = dbias != nullptr;
+  MSMC_REQUIRE(M < ((int64_t)1 << 31));
+  a.div_hw = make_fastdiv((uint32_t)(g.Hd * g.Wd));
+  a.div_w = make_fastdiv((uint32_t)g.Wd);
   a.gvec = (g.ld_dst % 4 == 0) && (reinterpret_cast<uintptr_t>(gout) & 15) == 0 &&
            (!xf_needs_aux(g.dst_xf) || ((g.ld_daux % 4 == 0) && (reinterpret_cast<uintptr_t>(gout_aux) & 15) == 0));
   // every split must own at least one position so that each partial tile is written
@@ -957,4 +1289,80 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
 #undef LAUNCH_WG_X
   MSMC_CHECK_LAUNCH();
   return launch_wgrad_reduce(g, workspace, eff_splits, dw, dbias, stream);
+}
+
+namespace {
+bool reuse_eligible(const msmc_conv_geom& g, int* tap_stride, int* n_taps, int* pad_rows) {
+  if (g.transposed || g.pad_reflect || g.sh != 1 || g.sw != 1) return false;
+  int ts, nt, pr;
+  if (g.Hs == 1 && g.Hd == 1 && g.KH == 1) { ts = g.dw; nt = g.KW; pr = g.pw; }
+  else if (g.KW == 1 && g.pw == 0 && g.Ws == g.Wd) { ts = g.dh * g.Ws; nt = g.KH; pr = g.ph * g.Ws; }
+  else return false;
+  if (nt < 2 || (nt - 1) * ts > RU_ROWS - UM_BM) return false;
+  *tap_stride = ts; *n_taps = nt; *pad_rows = pr;
+  return true;
+}
+}  // namespace
+
+extern "C" int msmc_conv_reuse_eligible(const msmc_conv_geom* gp) {
+  int a, b, c;
+  return gp && gp->Cs % UM_BK == 0 && reuse_eligible(*gp, &a, &b, &c) ? 1 : 0;
+}
+
+extern "C" int msmc_conv_forward_umma_reuse(const msmc_conv_geom* gp, const float* src, const float* src_aux,
+                                            const float* wimg, const float* bias, const float* residual,
+                                            const float* dst_aux, float* dst, int32_t split, int32_t BN,
+                                            void* stream) {
+  MSMC_REQUIRE(gp && src && wimg && dst);
+  const msmc_conv_geom& g = *gp;
+  ReuseArgs a;
+  MSMC_REQUIRE(reuse_eligible(g, &a.tap_stride, &a.n_taps, &a.pad_rows));
+  MSMC_REQUIRE(g.Cs % UM_BK == 0 && g.ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  MSMC_REQUIRE(!xf_needs_aux(g.src_xf) ||
+               (src_aux && g.ld_saux % 4 == 0 && (reinterpret_cast<uintptr_t>(src_aux) & 15) == 0));
+  MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || dst_aux);
+  MSMC_REQUIRE(BN == 32 || BN == 64 || BN == 128);
+  a.g = g; a.src = src; a.src_aux = src_aux; a.wimg = wimg; a.bias = bias; a.residual = residual;
+  a.dst_aux = dst_aux; a.dst = dst;
+  a.Ls = g.Hs * g.Ws; a.Ld = g.Hd * g.Wd;
+  a.tiles_per_batch = ceil_div(a.Ld, UM_BM);
+  {
+    const char* e = getenv("MSMC_REUSE_BASEOFF");
+    a.base_off_mode = e ? atoi(e) : 0;
+  }
+  dim3 grid((unsigned)(a.tiles_per_batch * g.B), (unsigned)ceil_div(g.Cd, BN));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int xfc = g.src_xf == MSMC_XF_NONE ? XFC_NONE
+                  : (g.src_xf == MSMC_XF_LRELU && g.src_slope > 0.f && g.src_slope < 1.f) ? XFC_LRELU : XFC_GENERIC;
+#define LAUNCH_RU_X(BN_, SPLIT_, NA_, NB_, X_)                                                                    \
+  do {                                                                                                            \
+    const size_t smem = 1024 + (size_t)(SPLIT_ ? 2 : 1) * ((size_t)NA_ * RU_ROWS * 128 + (size_t)NB_ * BN_ * 128) + \
+                        (2 * NA_ + 2 * NB_ + 1) * 8 + 16;                                                         \
+    cudaFuncSetAttribute(conv_umma_reuse_kernel<BN_, SPLIT_, NA_, NB_, X_>,                                       \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                 \
+    conv_umma_reuse_kernel<BN_, SPLIT_, NA_, NB_, X_><<<grid, RU_THREADS, smem, st>>>(a);                         \
+  } while (0)
+#define LAUNCH_RU(BN_, SPLIT_, NA_, NB_)                                       \
+  do {                                                                         \
+    if (xfc == XFC_NONE) LAUNCH_RU_X(BN_, SPLIT_, NA_, NB_, XFC_NONE);         \
+    else if (xfc == XFC_LRELU) LAUNCH_RU_X(BN_, SPLIT_, NA_, NB_, XFC_LRELU);  \
+    else LAUNCH_RU_X(BN_, SPLIT_, NA_, NB_, XFC_GENERIC);                      \
+  } while (0)
+  if (split) {
+    switch (BN) {
+      case 32: LAUNCH_RU(32, true, 3, 6); break;     // 144 KB + 48 KB
+      case 64: LAUNCH_RU(64, true, 3, 4); break;     // 144 KB + 64 KB
+      default: LAUNCH_RU(128, true, 2, 3); break;    //  96 KB + 96 KB
+    }
+  } else {
+    switch (BN) {
+      case 32: LAUNCH_RU(32, false, 3, 6); break;
+      case 64: LAUNCH_RU(64, false, 3, 6); break;
+      default: LAUNCH_RU(128, false, 3, 6); break;
+    }
+  }
+#undef LAUNCH_RU
+#undef LAUNCH_RU_X
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
 }

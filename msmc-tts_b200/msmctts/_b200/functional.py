@@ -15,6 +15,7 @@ from . import lib as L
 #   "fp32"             CUDA-core FMA kernels only
 CONV_MATH = os.environ.get("MSMC_CONV_MATH", "3xtf32")
 UMMA_MIN_ROWS = 256
+USE_TAP_REUSE = os.environ.get("MSMC_TAP_REUSE", "1") != "0"
 
 ConvCfg = namedtuple("ConvCfg", "KH KW sh sw dh dw ph pw reflect transposed wstr Cd pre_slope post out_hw")
 # wstr = element strides of the weight tensor for (kh, kw, cs, cd), cs = channels of the op's INPUT
@@ -116,8 +117,11 @@ def _launch_conv(src, w, wstr, bias, residual, dst, KH, KW, sh, sw, dh, dw, ph, 
         cs_op, cd_op = w_dims if w_role != 0 else (Cs, Cd)
         bn = L.load().msmc_umma_tile_n(Cd, B * Hd * Wd)
         img = _weight_image(w, KH * KW, cs_op, cd_op, w_role, split, bn)
-        L.call("msmc_conv_forward_umma", C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(img), L.ptr(bias), L.ptr(res),
-               L.ptr(daux), L.ptr(dst), split, bn, meta=meta)
+        name = "msmc_conv_forward_umma"
+        if USE_TAP_REUSE and L.load().msmc_conv_reuse_eligible(C.byref(g)):
+            name = "msmc_conv_forward_umma_reuse"     # stride-1: one staged operand tile serves every tap
+        L.call(name, C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(img), L.ptr(bias), L.ptr(res), L.ptr(daux),
+               L.ptr(dst), split, bn, meta=meta)
         return dst
     L.call("msmc_conv_forward", C.byref(g), L.ptr(src), L.ptr(saux), L.ptr(w), L.ptr(bias), L.ptr(res),
            L.ptr(daux), L.ptr(dst), meta=meta)

@@ -45,6 +45,8 @@ SIGNATURES = {
     "msmc_weight_image_elems": (C.c_int64, [_I32, _I32, _I32, _I32, _I32, _I32]),
     "msmc_weight_image": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "msmc_conv_forward_umma": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P]),
+    "msmc_conv_reuse_eligible": (C.c_int, [_G]),
+    "msmc_conv_forward_umma_reuse": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P]),
     "msmc_conv_wgrad_umma_workspace": (C.c_int64, [_G]),
     "msmc_conv_wgrad_umma": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "msmc_weight_norm_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I64, _I64, _I64, _P]),

@@ -216,6 +216,37 @@ def gen_autoencoder():
                                         encoder_indices=[i for i in o1["encoder_indices"]]))
 
 
+def gen_predictor():
+    P = R.ref("msmctts.networks.acoustic_models.multi_stage_predictor")
+    torch.manual_seed(18)
+    fft = dict(n_layers=1, n_head=2, d_k=64, d_v=64, d_model=64, d_inner=96, fft_conv1d_kernel=3,
+               fft_conv1d_padding=1, dropout=0.0, attn_dropout=0.0, fused_layernorm=False)
+    cfg = dict(n_symbols=[20, 5, 2], n_model_size=64, n_pred_size=32, n_pred_scale=[4, 1],
+               encoder_config=dict(fft, max_seq_len=40, name="phoneme_side"),
+               adaptor_config=dict(input_size=64, duration_predictor_filter_size=48,
+                                   duration_predictor_kernel_size=3, dropout=0.0, fused_layernorm=False),
+               decoder_config=dict(fft, max_seq_len=200, name="mel_side"))
+    m = P.MultiStagePredictor(**json.loads(json.dumps(cfg)))
+    m.train()
+    B, Lt = 2, 6
+    text = torch.stack([torch.randint(1, 20, (B, Lt)), torch.randint(1, 5, (B, Lt)), torch.randint(0, 2, (B, Lt))], -1)
+    text_length = torch.tensor([6, 4])
+    text[1, 4:] = 0
+    dur = torch.randint(2, 7, (B, Lt)).float()
+    dur[1, 4:] = 0
+    T = int(dur.sum(1).max())
+    fl1 = dur.sum(1).long()
+    fl0 = torch.ceil(fl1 / 4).long()
+    feat = [torch.randn(B, int(fl0.max()), 32), torch.randn(B, T, 32)]
+    out = m(text, text_length, dur=dur, feat=feat, feat_length=[fl0, fl1])
+    loss = sum((p * torch.linspace(-1, 1, p.numel()).view_as(p)).sum() for p in out["feat"]) + out["duration"].sum()
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    save("predictor.pt", dict(cfg=cfg, sd=clone_sd(m), text=text, text_length=text_length, dur=dur, feat=feat,
+                              feat_length=[fl0, fl1], preds=[p.detach() for p in out["feat"]],
+                              duration=out["duration"].detach(), loss=loss.detach(), grads=grads))
+
+
 def gen_keys():
     """state_dict names + shapes of the full CSMSC models (examples/csmsc/configs/msmc_vq_gan.yaml)."""
     C = R.ref("msmctts.utils.config")
@@ -255,4 +286,5 @@ if __name__ == "__main__":
     gen_discriminator()
     gen_melloss()
     gen_autoencoder()
+    gen_predictor()
     gen_keys()

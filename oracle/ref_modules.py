@@ -323,6 +323,63 @@ def msmcvqgan_forward(sd, cfg, mel, mel_length, warmup=False, window=None, train
     return out
 
 
+# ------------------------------------------------------------------------------------ multi-stage predictor
+def duration_predictor(sd, prefix, x, mask, p_drop=0.0, training=False):
+    """acoustic_models/transformer.py:521-534 DurationPredictor.forward"""
+    m = mask.to(x.dtype)
+    out = x * m
+    out = F.conv1d(out.transpose(1, 2), sd[prefix + "conv1d_1.weight"], sd[prefix + "conv1d_1.bias"], padding=1)
+    out = F.relu(out.transpose(1, 2))
+    out = F.layer_norm(out, (out.shape[-1],), sd[prefix + "layer_norm_1.weight"], sd[prefix + "layer_norm_1.bias"])
+    out = F.dropout(out, p_drop, training)
+    out = F.conv1d(out.transpose(1, 2), sd[prefix + "conv1d_2.weight"], sd[prefix + "conv1d_2.bias"], padding=1)
+    out = F.relu(out.transpose(1, 2))
+    out = F.layer_norm(out, (out.shape[-1],), sd[prefix + "layer_norm_2.weight"], sd[prefix + "layer_norm_2.bias"])
+    out = F.dropout(out, p_drop, training)
+    out = F.linear(out, sd[prefix + "linear_layer.weight"], sd[prefix + "linear_layer.bias"])
+    return (out * m).squeeze(-1)
+
+
+def multistage_predictor(sd, cfg, text, text_length, dur, feat, feat_length, training=True, prefix=""):
+    """acoustic_models/multi_stage_predictor.py:43-126 MultiStagePredictor.forward (teacher-forced: dur and feat
+    given, training mode, dropout off)"""
+    n_symbols, scales = cfg["n_symbols"], cfg["n_pred_scale"]
+    if isinstance(n_symbols, (list, tuple)):
+        out = sum(F.embedding(text[..., i].long(), sd["%sword_emb.%d.weight" % (prefix, i)], padding_idx=0)
+                  for i in range(len(n_symbols)))
+    else:
+        out = F.embedding(text.long(), sd[prefix + "word_emb.weight"], padding_idx=0)
+    pos = make_pos(text_length, text.shape[1])
+    out = fft_blocks(sd, prefix + "encoder.", out, pos, cfg["encoder_config"], training)
+    text_mask = pos.ne(0).unsqueeze(-1)
+    duration = duration_predictor(sd, prefix + "upsampler.duration_predictor.", out, text_mask)
+    reps = torch.round(dur.float()).long()
+    seqs = [torch.repeat_interleave(out[i], reps[i], dim=0) for i in range(out.shape[0])]
+    emb = torch.nn.utils.rnn.pad_sequence(seqs, batch_first=True)
+    down = []
+    for i, scale in enumerate(scales[::-1]):
+        emb = F.conv1d(emb.transpose(1, 2), sd["%sdownsamplers.%d.weight" % (prefix, i)],
+                       sd["%sdownsamplers.%d.bias" % (prefix, i)], padding=scale)
+        emb = F.avg_pool1d(emb, kernel_size=scale, stride=scale, ceil_mode=True).transpose(1, 2)
+        down.append(emb)
+    down = down[::-1]
+    preds, output = [], None
+    for i in range(len(scales)):
+        te = down[i]
+        pos = make_pos(feat_length[i], te.shape[1])
+        if i > 0:
+            pre = torch.cat((output, feat[i - 1]), dim=2)
+            pre = torch.repeat_interleave(pre, scales[i - 1], dim=1)[:, : te.shape[1]]
+            output = torch.cat((te, pre), dim=2)
+        else:
+            output = te
+        dp = "%sdecoders.%d." % (prefix, i)
+        output = F.linear(output, sd[dp + "0.weight"], sd[dp + "0.bias"])
+        output = fft_blocks(sd, dp + "1.", output, pos, cfg["decoder_config"], training)
+        preds.append(F.linear(output, sd[dp + "2.weight"], sd[dp + "2.bias"]))
+    return preds, duration
+
+
 # ------------------------------------------------------------------------------------------------ HifiGAN
 def resblock1(sd, prefix, x, kernel_size, dilations):
     """hifigan/common.py:43-51 ResBlock1.forward"""

@@ -160,6 +160,24 @@ def test_autoencoder_config1_analysis_synthesis(golden):
     close(out["mel_outputs"], g["mel_outputs"], tol=1e-4, msg="mel")
 
 
+def test_multistage_predictor_vs_reference(golden):
+    """BASELINE.json configs[4] call path (teacher-forced MultiStagePredictor), small config"""
+    from msmctts.networks.acoustic_models import MultiStagePredictor
+    g = golden("predictor.pt")
+    m = MultiStagePredictor(**copy.deepcopy(g["cfg"]))
+    m.load_state_dict(g["sd"])
+    m.to(DEV).train()
+    out = m(g["text"].to(DEV), g["text_length"].to(DEV), dur=g["dur"].to(DEV), feat=[f.to(DEV) for f in g["feat"]],
+            feat_length=[f.to(DEV) for f in g["feat_length"]])
+    for a, b in zip(out["feat"], g["preds"]):
+        close(a, b, tol=1e-4, msg="pred")
+    close(out["duration"], g["duration"], tol=1e-4, msg="duration")
+    loss = sum((p * torch.linspace(-1, 1, p.numel(), device=DEV).view_as(p)).sum() for p in out["feat"]) + \
+        out["duration"].sum()
+    loss.backward()
+    check_grads(m, g["grads"], tol=1e-3)
+
+
 def _csmsc_cfg(K):
     here = os.path.dirname(os.path.abspath(__file__))
     with open(os.path.join(here, "golden", "csmsc_config.json")) as f:

@@ -30,6 +30,9 @@ CASES = [
     ("Cd200 two N tiles", 2, 1, 300, 64, 200, 1, 3, (1, 1), (1, 1), (0, 1), False, None, "tanh", False),
     ("ffn-like Cs256 Cd512", 2, 1, 240, 256, 512, 1, 3, (1, 1), (1, 1), (0, 1), False, None, "relu", False),
     ("mpd (5,1) s(3,1) Cs64", 2, 90, 5, 64, 128, 5, 1, (3, 1), (1, 1), (2, 0), False, 0.2, "none", False),
+    ("mpd (5,1) s1 Cs64 W7", 2, 40, 7, 64, 64, 5, 1, (1, 1), (1, 1), (2, 0), False, 0.2, "none", False),
+    ("mpd (3,1) s1 Cs64 Cd1", 2, 30, 11, 64, 1, 3, 1, (1, 1), (1, 1), (1, 0), False, 0.2, "none", False),
+    ("k3 d1 L=1000 Cs32 (3 tiles/batch + tail)", 3, 1, 1000, 32, 48, 1, 3, (1, 1), (1, 1), (0, 1), False, None, "none", False),
     ("mrd 3x3 reflect s2 Cs32", 2, 40, 30, 32, 64, 3, 3, (2, 2), (1, 1), (1, 1), True, None, "lrelu", False),
     ("mrd 3x3 reflect s1 Cs64", 2, 21, 18, 64, 32, 3, 3, (1, 1), (1, 1), (1, 1), True, None, "lrelu", False),
 ]
@@ -81,6 +84,7 @@ def _run_case(case, tol, cmp=None):
     (y * wgt.to(DEV)).sum().backward()
     torch.cuda.synchronize()
     names = [n for n, _, _, _ in L.profile_end()]
+    names = [n.replace("msmc_conv_forward_umma_reuse", "msmc_conv_forward_umma") for n in names]
     assert "msmc_conv_forward_umma" in names, "the tensor-core kernel did not run: %s" % names
     assert "msmc_conv_wgrad_umma" in names, "the tensor-core weight gradient did not run: %s" % names
     close(y, y_ref, tol, "y")
@@ -105,6 +109,29 @@ def test_conv_umma_plain_tf32(case, monkeypatch):
     from msmctts._b200 import functional as Fn
     monkeypatch.setattr(Fn, "CONV_MATH", "tf32")
     _run_case(case, 1e-2, cmp=mean_close)
+
+
+def test_tap_reuse_kernel_is_selected_and_matches_plain_kernel(monkeypatch):
+    """stride-1 1-D conv: the tap-reuse kernel (shifted descriptors with base offset) must give the same numbers as
+    the per-tap staging kernel, which is already pinned against the CPU reference"""
+    from msmctts._b200 import functional as Fn
+    from msmctts._b200 import lib as L
+    monkeypatch.setattr(Fn, "CONV_MATH", "3xtf32")
+    gen = torch.Generator().manual_seed(11)
+    for (Ln, Ci, Co, K, d) in ((700, 64, 64, 11, 5), (333, 32, 96, 7, 3), (260, 256, 32, 3, 1)):
+        x = torch.randn(3, 1, Ln, Ci, generator=gen).to(DEV)
+        w = (torch.randn(1, K, Ci, Co, generator=gen) / (Ci * K) ** 0.5).to(DEV)
+        pad = (K * d - d) // 2
+        outs = []
+        for reuse in (True, False):
+            monkeypatch.setattr(Fn, "USE_TAP_REUSE", reuse)
+            L.profile_begin()
+            y = Fn.conv_cl(x, w, None, None, kernel=(1, K), dilation=(1, d), padding=(0, pad), pre_slope=0.1)
+            torch.cuda.synchronize()
+            names = [n for n, _, _, _ in L.profile_end()]
+            assert ("msmc_conv_forward_umma_reuse" in names) == reuse, names
+            outs.append(y)
+        close(outs[0], outs[1], 1e-5, "reuse vs plain L=%d" % Ln)
 
 
 def test_linear_umma(monkeypatch):
