@@ -192,6 +192,10 @@ int msmc_mel_double_bwd(const float* gout, const float* mel, float* gmel, int64_
 int msmc_log_clamp_fwd(const float* x, float* y, int64_t n, float clip, void* stream);
 int msmc_log_clamp_bwd(const float* gy, const float* x, float* gx, int64_t n, float clip, void* stream);
 
+/* forward STFT framing (torch.stft center / reflect padding, audio.py:399, stft_loss.py:88-99): gather the overlapping
+ * frames of x (B, L) into a dense (B*frames, win_p) matrix (columns >= win are zero) so the windowed DFT is one GEMM */
+int msmc_frame_unfold(const float* x, float* frames_out, int32_t B, int32_t L, int32_t frames, int32_t win,
+                      int32_t win_p, int32_t hop, int32_t pad, void* stream);
 /* backward of reflect-padded STFT framing (torch.stft center/reflect, audio.py:399; stft_loss.py:88-99): overlap-add
  * the per-frame time-domain gradients gframes (B, frames, win) onto x (B, L) and fold the reflected borders */
 int msmc_overlap_add_fold(const float* gframes, float* gx, int32_t B, int32_t frames, int32_t win, int32_t hop,

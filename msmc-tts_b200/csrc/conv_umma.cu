@@ -790,6 +790,8 @@ struct UmmaWgradArgs {
   int want_bias;
   int gvec;                // gout rows can be read with 16-byte loads
   FastDiv div_hw, div_w;   // m -> (b, rem) by Hd*Wd, rem -> (hd, wd) by Wd
+  int dry;                 // bring-up/profiling switch: 1 = producers skip loads and stores (MMA pipeline only),
+                           //                            2 = producers load and store but the MMA warp issues nothing
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
@@ -809,8 +811,29 @@ __device__ __forceinline__ uint32_t mn_off(int p, int c16) {
   return (uint32_t)p * 128u + (uint32_t)(((((c16 >> 1) ^ (p & 3)) << 1) | (c16 & 1)) << 4);
 }
 
-template <int BN, bool SPLIT, int STAGES, int XFC>
-__global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const UmmaWgradArgs a) {
+// 4x4 transpose across the 4 lanes that share a 16-byte chunk index (lane bits 3,4 = position sub-index):
+// in : lane p holds 4 channels of position p      out: lane p holds channel p at 4 consecutive positions
+__device__ __forceinline__ float4 transpose4_lanes(float4 x, int psub) {
+  {  // exchange the off-diagonal 2x2 blocks (partner: psub ^ 2)
+    const bool lo = psub < 2;
+    const float s0 = lo ? x.z : x.x, s1 = lo ? x.w : x.y;
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+    if (lo) { x.z = r0; x.w = r1; } else { x.x = r0; x.y = r1; }
+  }
+  {  // transpose inside each 2x2 block (partner: psub ^ 1)
+    const bool ev = (psub & 1) == 0;
+    const float s0 = ev ? x.y : x.x, s1 = ev ? x.w : x.z;
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 8), r1 = __shfl_xor_sync(0xffffffffu, s1, 8);
+    if (ev) { x.y = r0; x.w = r1; } else { x.x = r0; x.z = r1; }
+  }
+  return x;
+}
+
+// KMAJOR = true: the producers transpose both operands in registers (warp shuffles) and store ordinary K-major
+// SWIZZLE_128B tiles (rows = channels, 128 bytes = 32 positions), so the MMAs are the same K-major instructions as
+// the forward kernel; KMAJOR = false: MN-major SWIZZLE_128B_BASE32B operands straight from the row layout.
+template <int BN, bool SPLIT, int STAGES, int XFC, bool KMAJOR>
+__global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_umma_kernel(const UmmaWgradArgs a) {
   const msmc_conv_geom& g = a.g;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -880,37 +903,52 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const U
     const bool need_aux = NEED_AUX && xf_needs_aux(g.src_xf);
     const bool do_bias = a.want_bias && blockIdx.x == 0 && !is_a && nb_ok;
     const bool active = is_a ? true : nb_ok;
-    float4 v0[8], u0[8], v1[8], u1[8];         // two stages of loads in flight
+    // one stage of loads in flight per thread (two stages cost 128 registers here and spilled to local memory:
+    // the ncu capture in profiles/ showed 400 MB of DRAM writes from the spill traffic alone)
+    float4 v[8], u[8];
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
     int64_t m_next = mbeg + psub;              // position of row i = 0 of the next stage to gather
+    const bool small_w = g.Wd < 4;             // carry-propagating decode below needs Wd >= 4
 
-    auto gather = [&](float4 (&v)[8], float4 (&u)[8]) {
+    auto gather = [&]() {
+      // decode the first position with two multiply-shift divisions, walk the other seven by +4 with carries
+      int b = 0, hd = 0, wd = 0;
+      if (is_a && m_next < mend) {
+        const uint32_t mu = (uint32_t)m_next;
+        const uint32_t bb = fdiv(mu, a.div_hw);
+        const uint32_t rem = mu - bb * a.div_hw.d;
+        const uint32_t hh = fdiv(rem, a.div_w);
+        b = (int)bb; hd = (int)hh; wd = (int)(rem - hh * a.div_w.d);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int64_t m = m_next + 4 * i;
         const bool m_ok = m < mend;
         if (is_a) {
           bool ok = m_ok && rb_ok;
-          int64_t pix = 0;
+          int hs = hd * g.sh + kh * g.dh - g.ph;
+          int ws = wd * g.sw + kw * g.dw - g.pw;
+          if (g.pad_reflect) { hs = reflect1(hs, g.Hs); ws = reflect1(ws, g.Ws); }
+          else ok = ok && (unsigned)hs < (unsigned)g.Hs && (unsigned)ws < (unsigned)g.Ws;
           if (ok) {
-            const uint32_t mu = (uint32_t)m;
-            const uint32_t b = fdiv(mu, a.div_hw);
-            const uint32_t rem = mu - b * a.div_hw.d;
-            const uint32_t hd = fdiv(rem, a.div_w);
-            const uint32_t wd = rem - hd * a.div_w.d;
-            int hs = (int)hd * g.sh + kh * g.dh - g.ph;
-            int ws = (int)wd * g.sw + kw * g.dw - g.pw;
-            if (g.pad_reflect) { hs = reflect1(hs, g.Hs); ws = reflect1(ws, g.Ws); }
-            else ok = (unsigned)hs < (unsigned)g.Hs && (unsigned)ws < (unsigned)g.Ws;
-            pix = ((int64_t)b * g.Hs + hs) * g.Ws + ws;
-          }
-          if (ok) {
+            const int64_t pix = ((int64_t)b * g.Hs + hs) * g.Ws + ws;
             v[i] = __ldg(reinterpret_cast<const float4*>(a.src + pix * g.ld_src + cb * 32 + chunk * 4));
             if (NEED_AUX && need_aux)
               u[i] = __ldg(reinterpret_cast<const float4*>(a.src_aux + pix * g.ld_saux + cb * 32 + chunk * 4));
           } else {
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (NEED_AUX) u[i] = v[i];
+          }
+          // advance (b, hd, wd) by 4 positions
+          if (small_w) {
+            const uint32_t mu = (uint32_t)min(m + 4, mend - 1 > 0 ? mend - 1 : (int64_t)0);
+            const uint32_t bb = fdiv(mu, a.div_hw);
+            const uint32_t rem = mu - bb * a.div_hw.d;
+            const uint32_t hh = fdiv(rem, a.div_w);
+            b = (int)bb; hd = (int)hh; wd = (int)(rem - hh * a.div_w.d);
+          } else {
+            wd += 4;
+            if (wd >= g.Wd) { wd -= g.Wd; if (++hd == g.Hd) { hd = 0; ++b; } }
           }
         } else if (nb_ok) {
           if (m_ok && gvec_ok) {
@@ -934,11 +972,12 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const U
       m_next += 32;
     };
 
+    if (a.dry != 1) gather();
     int s = 0;
     uint32_t ph = 0;
-    auto produce = [&](int ks, float4 (&v)[8], float4 (&u)[8]) {
+    for (int ks = 0; ks < n_k; ++ks) {
       mbar_wait(&empty_bar[s], ph ^ 1u);
-      if (active) {
+      if (active && a.dry != 1) {
         uint8_t* base = (is_a ? sA + s * A_BYTES : sB + s * B_BYTES) + (uint32_t)blk * 4096u;
         constexpr int PLANE_A = A_PLANE, PLANE_B = B_PLANE;
 #pragma unroll
@@ -958,7 +997,15 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const U
             }
             if (do_bias) { bsum[0] += x.x; bsum[1] += x.y; bsum[2] += x.z; bsum[3] += x.w; }
           }
-          uint8_t* d = base + mn_off(p, chunk);
+          uint8_t* d;
+          if (KMAJOR) {
+            // after the transpose this lane owns channel row c = chunk*4 + psub, positions 4i .. 4i+3
+            x = transpose4_lanes(x, psub);
+            const int c = chunk * 4 + psub;
+            d = base + (uint32_t)(c >> 3) * 1024u + (uint32_t)(c & 7) * 128u + (uint32_t)((i ^ (c & 7)) << 4);
+          } else {
+            d = base + mn_off(p, chunk);
+          }
           if (SPLIT) {
             const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
             *reinterpret_cast<float4*>(d) = hi;
@@ -969,16 +1016,9 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const U
           }
         }
       }
-      if (ks + 2 < n_k) gather(v, u);
+      if (ks + 1 < n_k && a.dry != 1) gather();
       publish_and_arrive_warp(&full_bar[s]);
       if (++s == STAGES) { s = 0; ph ^= 1u; }
-    };
-
-    gather(v0, u0);
-    if (n_k > 1) gather(v1, u1);
-    for (int ks = 0; ks < n_k; ks += 2) {
-      produce(ks, v0, u0);
-      if (ks + 1 < n_k) produce(ks + 1, v1, u1);
     }
 
     // ================================= epilogue =================================
@@ -1016,7 +1056,7 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const U
     tc_fence_before();
   } else {
     // ================================= MMA issuer =================================
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (KMAJOR ? 0u : ((1u << 15) | (1u << 16))) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
     if ((tid & 31) == 0) {
       int s = 0;
@@ -1027,12 +1067,16 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_umma_kernel(const U
         const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
         const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-        for (int kg = 0; kg < 4; ++kg) {
-          // one MMA = 8 positions = two 4-row atoms (1 KB) per 32-channel block
-          const uint64_t a_hi = make_desc_mn(a_addr + kg * 1024), b_hi = make_desc_mn(b_addr + kg * 1024);
+        for (int kg = 0; kg < 4 && a.dry != 2; ++kg) {
+          // one MMA = 8 positions: MN-major -> two 4-row atoms (1 KB) per 32-channel block;
+          //                        K-major  -> 32 bytes further along every 128-byte channel row
+          const uint64_t a_hi = KMAJOR ? make_desc(a_addr + kg * 32) : make_desc_mn(a_addr + kg * 1024);
+          const uint64_t b_hi = KMAJOR ? make_desc(b_addr + kg * 32) : make_desc_mn(b_addr + kg * 1024);
           if (SPLIT) {
-            const uint64_t a_lo = make_desc_mn(a_addr + A_PLANE + kg * 1024);
-            const uint64_t b_lo = make_desc_mn(b_addr + B_PLANE + kg * 1024);
+            const uint64_t a_lo = KMAJOR ? make_desc(a_addr + A_PLANE + kg * 32)
+                                         : make_desc_mn(a_addr + A_PLANE + kg * 1024);
+            const uint64_t b_lo = KMAJOR ? make_desc(b_addr + B_PLANE + kg * 32)
+                                         : make_desc_mn(b_addr + B_PLANE + kg * 1024);
             umma_tf32(tmem_base, a_lo, b_hi, IDESC, (ks > 0 || kg > 0) ? 1u : 0u);
             umma_tf32(tmem_base, a_hi, b_lo, IDESC, 1u);
             umma_tf32(tmem_base, a_hi, b_hi, IDESC, 1u);
@@ -1211,7 +1255,10 @@ int umma_wgrad_splits(const msmc_conv_geom& g, int bn) {
   const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
   const int RB = g.KH * g.KW * (g.Cs / 32);
   const int64_t tiles = (int64_t)ceil_div(RB, 4) * ceil_div(g.Cd, bn);
-  int64_t s = ceil_div64((int64_t)num_sms() * 2, tiles);
+  // the producers are load-latency bound, so the BN <= 64 variants keep two CTAs per SM (2-stage rings); size the
+  // position split so that all CTAs are co-resident in one wave (a third, nearly empty wave cost 33 % before)
+  const int64_t slots = (int64_t)num_sms() * 2;
+  int64_t s = std::max<int64_t>(1, slots / tiles);
   const int64_t max_by_rows = std::max<int64_t>(1, M / 256);      // at least 8 stages per CTA
   if (s > max_by_rows) s = max_by_rows;
   const int64_t per = ((int64_t)g.KH * g.KW * g.Cs * g.Cd + g.Cd) * (int64_t)sizeof(float);
@@ -1246,6 +1293,11 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
   a.g = g; a.src = src; a.src_aux = src_aux; a.gout = gout; a.gout_aux = gout_aux; a.partial = workspace;
   a.rows_per_split = ceil_div64(ceil_div64(M, splits), 32) * 32;
   a.want_bias = dbias != nullptr;
+  {
+    const char* e = getenv("MSMC_WGRAD_DRY");
+    a.dry = e ? atoi(e) : 0;
+  }
+  static const int kmajor = [] { const char* e = getenv("MSMC_WGRAD_KMAJOR"); return e ? atoi(e) : 0; }();
   MSMC_REQUIRE(M < ((int64_t)1 << 31));
   a.div_hw = make_fastdiv((uint32_t)(g.Hd * g.Wd));
   a.div_w = make_fastdiv((uint32_t)g.Wd);
@@ -1262,9 +1314,15 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
   do {                                                                                                          \
     const size_t smem = 1024 + (size_t)ST_ * (SPLIT_ ? 2 : 1) * (4 * 4096 + (BN_ / 32) * 4096) +                \
                         (2 * ST_ + 1) * 8 + 16;                                                                 \
-    cudaFuncSetAttribute(conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_>,                                          \
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                               \
-    conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_><<<grid, UMF_THREADS, smem, st>>>(a);                           \
+    if (kmajor) {                                                                                               \
+      cudaFuncSetAttribute(conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_, true>,                                  \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                             \
+      conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_, true><<<grid, UMF_THREADS, smem, st>>>(a);                   \
+    } else {                                                                                                    \
+      cudaFuncSetAttribute(conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_, false>,                                 \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                             \
+      conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_, false><<<grid, UMF_THREADS, smem, st>>>(a);                  \
+    }                                                                                                           \
   } while (0)
 #define LAUNCH_WG(BN_, SPLIT_, ST_)                                        \
   do {                                                                     \
@@ -1274,14 +1332,14 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
   } while (0)
   if (split) {
     switch (bn) {
-      case 32: LAUNCH_WG(32, true, 4); break;
-      case 64: LAUNCH_WG(64, true, 4); break;
-      default: LAUNCH_WG(128, true, 3); break;
+      case 32: LAUNCH_WG(32, true, 2); break;       // 2 x 40 KB, two CTAs per SM
+      case 64: LAUNCH_WG(64, true, 2); break;       // 2 x 48 KB, two CTAs per SM
+      default: LAUNCH_WG(128, true, 3); break;      // 3 x 64 KB
     }
   } else {
     switch (bn) {
-      case 32: LAUNCH_WG(32, false, 4); break;
-      case 64: LAUNCH_WG(64, false, 4); break;
+      case 32: LAUNCH_WG(32, false, 4); break;      // 4 x 20 KB
+      case 64: LAUNCH_WG(64, false, 4); break;      // 4 x 24 KB
       default: LAUNCH_WG(128, false, 4); break;
     }
   }

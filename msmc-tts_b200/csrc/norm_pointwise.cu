@@ -278,6 +278,27 @@ __global__ void overlap_add_fold_kernel(const float* __restrict__ gf, float* __r
   }
 }
 
+// STFT framing: frames[b*F + f][k] = x[b][reflect(f*hop + k - pad)] for k < win, 0 for win <= k < win_p.
+// Materialising the (B*frames, win_p) matrix (a few MB) turns the windowed DFT into one tensor-core GEMM.
+__global__ void frame_unfold_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int L, int frames,
+                                    int win, int win_p, int hop, int pad) {
+  const int64_t total = (int64_t)B * frames * win_p;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e % win_p);
+    const int64_t r = e / win_p;
+    const int f = (int)(r % frames), b = (int)(r / frames);
+    float v = 0.f;
+    if (k < win) {
+      int i = f * hop + k - pad;
+      if (i < 0) i = -i;
+      if (i >= L) i = 2 * (L - 1) - i;
+      v = x[(int64_t)b * L + i];
+    }
+    out[e] = v;
+  }
+}
+
 inline int ew_blocks(int64_t n) { return (int)std::min<int64_t>(ceil_div64(n, 256), (int64_t)num_sms() * 16); }
 
 constexpr int LN_BWD_MAX_BLOCKS = 296;
@@ -387,6 +408,15 @@ extern "C" int msmc_overlap_add_fold(const float* gframes, float* gx, int32_t B,
   MSMC_REQUIRE(gframes && gx && B > 0 && frames > 0 && win > 0 && hop > 0 && L > 0 && pad >= 0 && pad < L);
   overlap_add_fold_kernel<<<ew_blocks((int64_t)B * L), 256, 0, (cudaStream_t)stream>>>(gframes, gx, B, frames, win,
                                                                                       hop, L, pad);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+extern "C" int msmc_frame_unfold(const float* x, float* frames_out, int32_t B, int32_t L, int32_t frames, int32_t win,
+                                 int32_t win_p, int32_t hop, int32_t pad, void* stream) {
+  MSMC_REQUIRE(x && frames_out && B > 0 && L > 1 && frames > 0 && win > 0 && win_p >= win && hop > 0 && pad >= 0 &&
+               pad < L);
+  frame_unfold_kernel<<<ew_blocks((int64_t)B * frames * win_p), 256, 0, (cudaStream_t)stream>>>(
+      x, frames_out, B, L, frames, win, win_p, hop, pad);
   MSMC_CHECK_LAUNCH();
   return MSMC_OK;
 }

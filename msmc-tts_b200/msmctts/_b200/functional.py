@@ -338,13 +338,23 @@ class _StftFn(torch.autograd.Function):
     conv-transpose over hop phases."""
 
     @staticmethod
-    def forward(ctx, x, basis, basis_t, hop, pad):
+    def forward(ctx, x, basis, basis_t, hop, pad, win):
         B, Ln = x.shape
-        win, F2 = basis.shape
+        win_p, F2 = basis.shape                  # basis rows are zero-padded from win to a multiple of 32
         frames = (Ln + 2 * pad - win) // hop + 1
-        y = torch.empty((B, 1, frames, F2), dtype=torch.float32, device=x.device)
-        _launch_conv(x.reshape(B, 1, Ln, 1), basis, (0, F2, F2, 1), None, None, y, 1, win, 1, hop, 1, 1, 0, pad,
-                     True, False)
+        x = x.contiguous()
+        if CONV_MATH != "fp32" and B * frames >= UMMA_MIN_ROWS and win_p % 32 == 0:
+            # unfold (a few MB) + one tensor-core GEMM over the frames
+            fr = torch.empty((B * frames, 1, 1, win_p), dtype=torch.float32, device=x.device)
+            L.require_cuda(x)
+            L.call("msmc_frame_unfold", L.ptr(x), L.ptr(fr), B, Ln, frames, win, win_p, hop, pad)
+            y = torch.empty((B * frames, 1, 1, F2), dtype=torch.float32, device=x.device)
+            _launch_conv(fr, basis, (win_p * F2, win_p * F2, F2, 1), None, None, y, 1, 1, 1, 1, 1, 1, 0, 0, False,
+                         False)
+        else:
+            y = torch.empty((B, 1, frames, F2), dtype=torch.float32, device=x.device)
+            _launch_conv(x.reshape(B, 1, Ln, 1), basis, (0, F2, F2, 1), None, None, y, 1, win, 1, hop, 1, 1, 0, pad,
+                         True, False)
         ctx.save_for_backward(basis_t)
         ctx.dims = (B, Ln, win, F2, frames, hop, pad)
         return y.reshape(B, frames, F2)
@@ -359,12 +369,13 @@ class _StftFn(torch.autograd.Function):
                      1, 1, 1, 1, 1, 1, 0, 0, False, False)
         gx = torch.empty((B, Ln), dtype=torch.float32, device=gy.device)
         L.call("msmc_overlap_add_fold", L.ptr(gframes), L.ptr(gx), B, frames, win, hop, Ln, pad)
-        return gx, None, None, None, None
+        return gx, None, None, None, None, None
 
 
-def stft_frames(x, basis, basis_t, hop, pad):
-    """x (B, L), basis (win, 2Fp) = hann * [cos | 0 | -sin | 0], basis_t its transpose -> (B, frames, 2Fp)"""
-    return _StftFn.apply(x, basis, basis_t, int(hop), int(pad))
+def stft_frames(x, basis, basis_t, hop, pad, win):
+    """x (B, L); basis (win_p, 2Fp) = hann * [cos | 0 | -sin | 0] with rows >= win zero; basis_t (2Fp, win) the
+    transpose of its first win rows -> (B, frames, 2Fp)"""
+    return _StftFn.apply(x, basis, basis_t, int(hop), int(pad), int(win))
 
 
 # ------------------------------------------------------------------------------------------ weight prep

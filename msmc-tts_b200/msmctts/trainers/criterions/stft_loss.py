@@ -44,7 +44,7 @@ class MelLoss(nn.Module):
         self.n_freq = fft_size // 2 + 1
         basis, self.left, self.n_freq_pad = dft_basis(fft_size, win_size, normalized=False)
         self.register_buffer("basis", basis, persistent=False)
-        self.register_buffer("basis_t", basis.t().contiguous(), persistent=False)
+        self.register_buffer("basis_t", basis[:win_size].t().contiguous(), persistent=False)
         self.register_buffer("mel_basis", mel_filterbank_slaney(sample_rate, fft_size, num_mels, 0,
                                                                 sample_rate // 2), persistent=False)
 
@@ -52,7 +52,7 @@ class MelLoss(nn.Module):
         """y (B, L) -> log-mel (B, frames, num_mels)"""
         B, L = y.shape
         pad = int((self.fft_size - self.hop_size) / 2) - self.left
-        spec = Fn.stft_frames(y, self.basis, self.basis_t, self.hop_size, pad)
+        spec = Fn.stft_frames(y, self.basis, self.basis_t, self.hop_size, pad, self.win_size)
         mag = Fn.spec_magnitude(spec, 1e-9, True, self.n_freq)
         mel = Fn.linear_cl(mag, self.mel_basis)
         return Fn.log_clamp(mel, 1e-5)

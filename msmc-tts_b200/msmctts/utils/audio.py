@@ -43,9 +43,10 @@ def dft_basis(n_fft, win_length, normalized, dtype=torch.float32):
     ang = 2.0 * np.pi * np.outer(k, f) / n_fft
     win = torch.hann_window(win_length, dtype=torch.float64).numpy()     # periodic, like the reference
     scale = (1.0 / math.sqrt(n_fft)) if normalized else 1.0
-    basis = np.zeros((win_length, 2 * Fp))
-    basis[:, :F] = np.cos(ang) * win[:, None] * scale
-    basis[:, Fp:Fp + F] = -np.sin(ang) * win[:, None] * scale
+    win_p = (win_length + 31) // 32 * 32           # zero rows: the unfolded-frame GEMM wants K % 32 == 0
+    basis = np.zeros((win_p, 2 * Fp))
+    basis[:win_length, :F] = np.cos(ang) * win[:, None] * scale
+    basis[:win_length, Fp:Fp + F] = -np.sin(ang) * win[:, None] * scale
     return torch.from_numpy(basis).to(dtype), left, Fp
 
 
@@ -76,7 +77,7 @@ class TorchSTFT(nn.Module):
         self.n_freq = fft_size // 2 + 1
         basis, self.left, self.n_freq_pad = dft_basis(fft_size, win_size, normalized)
         self.register_buffer("basis", basis, persistent=False)          # (win, 2Fp): GEMM layout [tap][1][2Fp]
-        self.register_buffer("basis_t", basis.t().contiguous(), persistent=False)
+        self.register_buffer("basis_t", basis[:win_size].t().contiguous(), persistent=False)
         self.mel_scale = MelScale(self.n_freq, sample_rate, n_stft=self.n_freq) if mel_scale else None
 
     def spectrum_cl(self, x, center=True, pad=None):
@@ -84,7 +85,7 @@ class TorchSTFT(nn.Module):
         B, L = x.shape
         p = (self.fft_size // 2 if center else 0) if pad is None else pad
         p = p - self.left
-        return Fn.stft_frames(x, self.basis, self.basis_t, self.hop_size, p)
+        return Fn.stft_frames(x, self.basis, self.basis_t, self.hop_size, p, self.win_size)
 
     def transform_cl(self, x):
         """x (B, L) -> (B, frames, F, C) with C = 2 ('double': lin, log), else 1"""
