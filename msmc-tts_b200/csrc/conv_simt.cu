@@ -463,6 +463,162 @@ __global__ void __launch_bounds__(NTHREADS) conv_wgrad_kernel(const WgradArgs a)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient of the few-channel convolutions (first layers of the period / resolution discriminators:
+// 1-8 input channels, 4-16 output channels, 10^5-10^6 positions).  The GEMM tile kernels above waste >90 % of a
+// 128 x 16 tile on these; here the whole dW (plus the bias row) is one accumulator set per CTA:
+//   stage 128 positions transposed in shared memory  s_x[k][p] (k = (tap, cs), row Ktot = ones -> bias),  s_g[cd][p]
+//   thread (group, o) accumulates  dW[o] += sum_p s_x[k(o)][p] * s_g[cd(o)][p]  over its group's positions
+// Partials per position-slice use the same [Ktot*Cd + Cd] workspace rows and second pass as the other kernels.
+// ------------------------------------------------------------------------------------------------
+constexpr int SW_TP = 128;               // positions per staged tile
+constexpr int SW_PITCH = SW_TP + 4;      // +4 floats: 16-byte aligned rows, rows land 4 banks apart
+constexpr int SW_THREADS = 256;
+constexpr int SW_MAX_NO = 5;             // outputs per thread when (Ktot+1)*Cd > 256
+
+struct SmallWgradArgs {
+  msmc_conv_geom g;
+  const float* src;
+  const float* src_aux;
+  const float* gout;
+  const float* gout_aux;
+  float* partial;          // [splits][Ktot*Cd + Cd]
+  int64_t rows_per_split;  // multiple of SW_TP
+  int groups;              // position groups per tile (power of two, 1..8)
+  int outs_per_thread;     // 1..SW_MAX_NO
+};
+
+__global__ void __launch_bounds__(SW_THREADS) conv_wgrad_small_kernel(const SmallWgradArgs a) {
+  const msmc_conv_geom& g = a.g;
+  extern __shared__ __align__(16) float sw_smem[];
+  const int Ktot = g.KH * g.KW * g.Cs;
+  const int O = (Ktot + 1) * g.Cd;
+  float* s_x = sw_smem;                               // [(Ktot + 1)][SW_PITCH]
+  float* s_g = sw_smem + (Ktot + 1) * SW_PITCH;       // [Cd][SW_PITCH]
+  const int tid = threadIdx.x;
+  const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
+  const int64_t mbeg = (int64_t)blockIdx.x * a.rows_per_split;
+  const int64_t mend = min(M, mbeg + a.rows_per_split);
+  const bool need_aux = xf_needs_aux(g.src_xf);
+  const bool gneed_aux = xf_needs_aux(g.dst_xf);
+
+  const int tg = SW_THREADS / a.groups;               // threads per group
+  const int grp = tid / tg, to = tid - grp * tg;
+  const int span = SW_TP / a.groups;                  // positions per group and tile (multiple of 4)
+  int xrow[SW_MAX_NO], grow[SW_MAX_NO];
+  float acc[SW_MAX_NO];
+#pragma unroll
+  for (int j = 0; j < SW_MAX_NO; ++j) {
+    const int o = to + j * tg;
+    const bool ok = j < a.outs_per_thread && o < O;
+    const int k = ok ? o / g.Cd : 0;
+    xrow[j] = ok ? k * SW_PITCH : -1;
+    grow[j] = ok ? (o - k * g.Cd) * SW_PITCH : 0;
+    acc[j] = 0.f;
+  }
+
+  const int lp = tid & (SW_TP - 1);                   // position this thread gathers
+  const int lk = tid / SW_TP;                         // 0 / 1: even / odd reduction rows
+  const unsigned hw = (unsigned)(g.Hd * g.Wd);
+  for (int64_t m0 = mbeg; m0 < mend; m0 += SW_TP) {
+    // ---- stage the source patch: one position per thread, every other (tap, channel) row ----
+    {
+      const int64_t m = m0 + lp;
+      const bool m_ok = m < mend;
+      int b = 0, hd = 0, wd = 0;
+      if (m_ok) {
+        b = (int)((unsigned)m / hw);
+        const int rem = (int)((unsigned)m - (unsigned)b * hw);
+        hd = (int)((unsigned)rem / (unsigned)g.Wd);
+        wd = rem - hd * g.Wd;
+      }
+      int t = 0, c = lk;                              // k = t * Cs + c, advanced by 2 per iteration
+      while (c >= g.Cs) { c -= g.Cs; ++t; }
+      for (int k = lk; k < Ktot; k += 2) {
+        float v = 0.f;
+        if (m_ok) {
+          const int kh = t / g.KW, kw = t - kh * g.KW;
+          int hs, ws;
+          if (src_coord(g, hd, wd, kh, kw, hs, ws)) {
+            const int64_t off = ((int64_t)b * g.Hs + hs) * g.Ws + ws;
+            v = __ldg(a.src + off * g.ld_src + c);
+            if (g.src_xf != MSMC_XF_NONE)
+              v = apply_xf(g.src_xf, g.src_slope, v, need_aux ? __ldg(a.src_aux + off * g.ld_saux + c) : 0.f);
+          }
+        }
+        s_x[k * SW_PITCH + lp] = v;
+        c += 2;
+        while (c >= g.Cs) { c -= g.Cs; ++t; }
+      }
+      if (lk == 0) s_x[Ktot * SW_PITCH + lp] = m_ok ? 1.f : 0.f;
+    }
+    // ---- stage the output gradient transposed ----
+    for (int e = tid; e < SW_TP * g.Cd; e += SW_THREADS) {
+      const int p = e / g.Cd, cd = e - p * g.Cd;
+      const int64_t m = m0 + p;
+      float v = 0.f;
+      if (m < mend) {
+        v = __ldg(a.gout + m * g.ld_dst + cd);
+        if (g.dst_xf != MSMC_XF_NONE)
+          v = apply_xf(g.dst_xf, g.dst_slope, v, gneed_aux ? __ldg(a.gout_aux + m * g.ld_daux + cd) : 0.f);
+      }
+      s_g[cd * SW_PITCH + p] = v;
+    }
+    __syncthreads();
+    const int p0 = grp * span;
+#pragma unroll
+    for (int j = 0; j < SW_MAX_NO; ++j) {
+      if (xrow[j] >= 0) {
+        const float* xr = s_x + xrow[j] + p0;
+        const float* gr = s_g + grow[j] + p0;
+        float s = acc[j];
+        for (int p = 0; p < span; p += 4) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xr + p);
+          const float4 g4 = *reinterpret_cast<const float4*>(gr + p);
+          s = fmaf(x4.x, g4.x, s); s = fmaf(x4.y, g4.y, s); s = fmaf(x4.z, g4.z, s); s = fmaf(x4.w, g4.w, s);
+        }
+        acc[j] = s;
+      }
+    }
+    __syncthreads();
+  }
+
+  float* part = a.partial + (int64_t)blockIdx.x * O;
+  if (a.groups == 1) {
+#pragma unroll
+    for (int j = 0; j < SW_MAX_NO; ++j)
+      if (xrow[j] >= 0) part[to + j * tg] = acc[j];
+  } else {
+    // fixed-order sum over the position groups (outs_per_thread == 1 here)
+    float* s_red = sw_smem;                            // [groups][tg], groups * tg = 256 floats
+    s_red[grp * tg + to] = acc[0];
+    __syncthreads();
+    if (grp == 0 && to < O) {
+      float s = 0.f;
+      for (int q = 0; q < a.groups; ++q) s += s_red[q * tg + to];
+      part[to] = s;
+    }
+  }
+}
+
+bool small_wgrad_plan(const msmc_conv_geom& g, int* groups, int* outs_per_thread) {
+  if (g.transposed) return false;
+  const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
+  if (Ktot > 80 || g.Cs > 8 || g.Cd > 16) return false;
+  const int O = (int)(Ktot + 1) * g.Cd;
+  if (O > SW_THREADS * SW_MAX_NO) return false;
+  int ng = 1;
+  while (ng < 8 && SW_THREADS / (ng * 2) >= O) ng *= 2;
+  *groups = ng;
+  *outs_per_thread = ng > 1 ? 1 : ceil_div(O, SW_THREADS);
+  return true;
+}
+int small_wgrad_splits(const msmc_conv_geom& g) {
+  const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(M, 2 * SW_TP), (int64_t)num_sms() * 4));
+}
+
 __global__ void wgrad_reduce_kernel(const msmc_conv_geom g, const float* __restrict__ partial, int splits,
                                     float* __restrict__ dw, float* __restrict__ dbias) {
   const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
@@ -666,7 +822,9 @@ extern "C" int64_t msmc_conv_wgrad_workspace(const msmc_conv_geom* gp) {
   if (!gp) return -1;
   const msmc_conv_geom& g = *gp;
   const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
-  return (int64_t)wgrad_splits(g) * (Ktot * g.Cd + g.Cd) * (int64_t)sizeof(float);
+  int ng, no;
+  const int splits = msmc::small_wgrad_plan(g, &ng, &no) ? msmc::small_wgrad_splits(g) : wgrad_splits(g);
+  return (int64_t)splits * (Ktot * g.Cd + g.Cd) * (int64_t)sizeof(float);
 }
 
 extern "C" int msmc_conv_wgrad(const msmc_conv_geom* gp, const float* src, const float* src_aux,
@@ -678,10 +836,31 @@ extern "C" int msmc_conv_wgrad(const msmc_conv_geom* gp, const float* src, const
   MSMC_REQUIRE((int64_t)g.B * g.Hd * g.Wd < ((int64_t)1 << 31) && (int64_t)g.B * g.Hs * g.Ws < ((int64_t)1 << 31));
   MSMC_REQUIRE(!xf_needs_aux(g.src_xf) || src_aux);
   MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || gout_aux);
-  const int splits = wgrad_splits(g);
   const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
-  MSMC_REQUIRE(workspace_bytes >= (int64_t)splits * (Ktot * g.Cd + g.Cd) * (int64_t)sizeof(float));
   const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    SmallWgradArgs sa;
+    if (small_wgrad_plan(g, &sa.groups, &sa.outs_per_thread)) {
+      const int ssplits = small_wgrad_splits(g);
+      MSMC_REQUIRE(workspace_bytes >= (int64_t)ssplits * (Ktot * g.Cd + g.Cd) * (int64_t)sizeof(float));
+      sa.g = g; sa.src = src; sa.src_aux = src_aux; sa.gout = gout; sa.gout_aux = gout_aux; sa.partial = workspace;
+      sa.rows_per_split = ceil_div64(ceil_div64(M, ssplits), SW_TP) * SW_TP;
+      const int eff = (int)ceil_div64(M, sa.rows_per_split);
+      const size_t smem = (size_t)std::max<int64_t>((Ktot + 1 + g.Cd) * SW_PITCH, SW_THREADS) * sizeof(float);
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaFuncSetAttribute(conv_wgrad_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_done = true;
+      }
+      conv_wgrad_small_kernel<<<eff, SW_THREADS, smem, st>>>(sa);
+      MSMC_CHECK_LAUNCH();
+      // the bias row is always produced; the second pass ignores it when dbias is null
+      return launch_wgrad_reduce(g, workspace, eff, dw, dbias, stream);
+    }
+  }
+  const int splits = wgrad_splits(g);
+  MSMC_REQUIRE(workspace_bytes >= (int64_t)splits * (Ktot * g.Cd + g.Cd) * (int64_t)sizeof(float));
   WgradArgs a;
   a.g = g; a.src = src; a.src_aux = src_aux; a.gout = gout; a.gout_aux = gout_aux;
   a.partial = workspace;
@@ -691,7 +870,6 @@ extern "C" int msmc_conv_wgrad(const msmc_conv_geom* gp, const float* src, const
   a.want_bias = dbias != nullptr;
   const int bn = pick_bn(g.Cd);
   dim3 grid((unsigned)ceil_div64(Ktot, BM), (unsigned)ceil_div(g.Cd, bn), (unsigned)splits);
-  cudaStream_t st = (cudaStream_t)stream;
   switch (bn) {
     case 16: conv_wgrad_kernel<16><<<grid, NTHREADS, 0, st>>>(a); break;
     case 32: conv_wgrad_kernel<32><<<grid, NTHREADS, 0, st>>>(a); break;

@@ -51,6 +51,8 @@ CONV_CASES = [
     ("mpd first Ci=1", 2, 100, 5, 1, 4, 5, 1, (3, 1), (1, 1), (2, 0), False, None, "none", False, True, True),
     ("mrd 3x3 reflect s1", 2, 20, 17, 2, 4, 3, 3, (1, 1), (1, 1), (1, 1), True, None, "lrelu", False, True, True),
     ("mrd 3x3 reflect s2", 2, 21, 18, 8, 16, 3, 3, (2, 2), (1, 1), (1, 1), True, None, "lrelu", False, True, True),
+    ("mrd first layer many rows", 2, 200, 31, 2, 4, 3, 3, (1, 1), (1, 1), (1, 1), False, None, "lrelu", False, True, True),
+    ("mrd 4->8 s(1,2) many rows", 2, 90, 61, 4, 8, 3, 3, (1, 2), (1, 1), (1, 1), False, None, "lrelu", False, True, True),
     ("stft-like k60 s15 reflect", 2, 1, 400, 1, 62, 1, 60, (1, 15), (1, 1), (0, 30), True, None, "none", False, False, False),
     ("downsampler k9 p4", 2, 1, 44, 40, 40, 1, 9, (1, 1), (1, 1), (0, 4), False, None, "none", False, False, True),
 ]
