@@ -283,6 +283,94 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(const ConvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Few-channel convolutions (<= 16 input and <= 16 output channels: the first layers of the discriminators and
+// their data gradients).  A 128 x 16 x 16 GEMM tile is mostly padding for them, so this kernel is direct: one
+// thread per destination position holds all CDP output channels in registers, the whole weight sits in shared
+// memory as [tap][cs][CDP] and is read with warp-broadcast 16-byte loads (one LDS.128 per 4 FMAs), the source
+// patch comes through L1 (neighbouring threads read neighbouring pixels).  Forward and conv-transpose forms share
+// src_coord(); taps that fall on padding or between stride phases are skipped.
+// ------------------------------------------------------------------------------------------------
+constexpr int DS_THREADS = 128;
+constexpr int DS_MAX_W = 2304;   // (tap, cs, CDP) weight floats in shared memory
+
+template <int CDP>
+__global__ void __launch_bounds__(DS_THREADS) conv_direct_small_kernel(const ConvArgs a) {
+  const msmc_conv_geom& g = a.g;
+  __shared__ __align__(16) float s_w[DS_MAX_W];
+  const int T = g.KH * g.KW;
+  for (int e = threadIdx.x; e < T * g.Cs * CDP; e += DS_THREADS) {
+    const int n = e % CDP;
+    const int r = e / CDP;
+    const int c = r % g.Cs, t = r / g.Cs;
+    const int kh = t / g.KW, kw = t - kh * g.KW;
+    s_w[e] = n < g.Cd ? __ldg(a.w + kh * g.ws_kh + kw * g.ws_kw + c * g.ws_cs + (int64_t)n * g.ws_cd) : 0.f;
+  }
+  __syncthreads();
+  const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
+  const int64_t m = (int64_t)blockIdx.x * DS_THREADS + threadIdx.x;
+  if (m >= M) return;
+  const unsigned hw = (unsigned)(g.Hd * g.Wd);
+  const int b = (int)((unsigned)m / hw);
+  const int rem = (int)((unsigned)m - (unsigned)b * hw);
+  const int hd = (int)((unsigned)rem / (unsigned)g.Wd), wd = rem - hd * g.Wd;
+  const bool need_aux = xf_needs_aux(g.src_xf);
+
+  float acc[CDP];
+#pragma unroll
+  for (int j = 0; j < CDP; ++j) acc[j] = 0.f;
+  for (int kh = 0; kh < g.KH; ++kh)
+    for (int kw = 0; kw < g.KW; ++kw) {
+      int hs, ws;
+      if (!src_coord(g, hd, wd, kh, kw, hs, ws)) continue;
+      const int64_t off = ((int64_t)b * g.Hs + hs) * g.Ws + ws;
+      const float* sp = a.src + off * g.ld_src;
+      const float* ap = need_aux ? a.src_aux + off * g.ld_saux : nullptr;
+      const float* wt = s_w + (kh * g.KW + kw) * g.Cs * CDP;
+      for (int c = 0; c < g.Cs; ++c) {
+        float v = __ldg(sp + c);
+        if (g.src_xf != MSMC_XF_NONE) v = apply_xf(g.src_xf, g.src_slope, v, need_aux ? __ldg(ap + c) : 0.f);
+        const float4* w4 = reinterpret_cast<const float4*>(wt + c * CDP);
+#pragma unroll
+        for (int j = 0; j < CDP / 4; ++j) {
+          const float4 w = w4[j];
+          acc[4 * j + 0] = fmaf(v, w.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(v, w.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v, w.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(v, w.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  const bool dneed_aux = xf_needs_aux(g.dst_xf);
+#pragma unroll
+  for (int n = 0; n < CDP; ++n) {
+    if (n < g.Cd) {
+      float v = acc[n];
+      if (a.bias) v += __ldg(a.bias + n);
+      if (g.dst_xf != MSMC_XF_NONE)
+        v = apply_xf(g.dst_xf, g.dst_slope, v, dneed_aux ? __ldg(a.dst_aux + m * g.ld_daux + n) : 0.f);
+      if (a.residual) v += __ldg(a.residual + m * g.ld_res + n);
+      acc[n] = v;
+    }
+  }
+  float* out = a.dst + m * g.ld_dst;
+  if ((g.Cd & 3) == 0 && (g.ld_dst & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dst) & 15) == 0) {
+#pragma unroll
+    for (int n = 0; n < CDP; n += 4)
+      if (n < g.Cd) *reinterpret_cast<float4*>(out + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+  } else {
+#pragma unroll
+    for (int n = 0; n < CDP; ++n)
+      if (n < g.Cd) out[n] = acc[n];
+  }
+}
+
+bool direct_small_eligible(const msmc_conv_geom& g) {
+  if (g.Cs > 16 || g.Cd > 16) return false;
+  const int cdp = g.Cd <= 4 ? 4 : (g.Cd <= 8 ? 8 : 16);
+  return (int64_t)g.KH * g.KW * g.Cs * cdp <= DS_MAX_W;
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight gradient:  dW[(tap,cs), cd] = sum_m  xf(src)[m,(tap,cs)] * xf(gout)[m, cd]
 // ------------------------------------------------------------------------------------------------
 struct WgradArgs {
@@ -607,7 +695,7 @@ bool small_wgrad_plan(const msmc_conv_geom& g, int* groups, int* outs_per_thread
   const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
   if (Ktot > 80 || g.Cs > 8 || g.Cd > 16) return false;
   const int O = (int)(Ktot + 1) * g.Cd;
-  if (O > SW_THREADS * SW_MAX_NO) return false;
+  if (O > 2 * SW_THREADS) return false;          // beyond two outputs per thread the 128 x 16 tile kernel wins
   int ng = 1;
   while (ng < 8 && SW_THREADS / (ng * 2) >= O) ng *= 2;
   *groups = ng;
@@ -782,13 +870,22 @@ extern "C" int msmc_conv_forward(const msmc_conv_geom* gp, const float* src, con
   a.vec_src = (g.Cs % 8 == 0) && (g.ld_src % 4 == 0) && aligned16(src) &&
               (!xf_needs_aux(g.src_xf) || ((g.ld_saux % 4 == 0) && aligned16(src_aux)));
   a.b_kmajor = (g.ws_cd != 1 && g.ws_cs == 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (direct_small_eligible(g)) {
+    const int64_t Mall = (int64_t)g.B * g.Hd * g.Wd;
+    const unsigned blocks = (unsigned)ceil_div64(Mall, DS_THREADS);
+    if (g.Cd <= 4) conv_direct_small_kernel<4><<<blocks, DS_THREADS, 0, st>>>(a);
+    else if (g.Cd <= 8) conv_direct_small_kernel<8><<<blocks, DS_THREADS, 0, st>>>(a);
+    else conv_direct_small_kernel<16><<<blocks, DS_THREADS, 0, st>>>(a);
+    MSMC_CHECK_LAUNCH();
+    return MSMC_OK;
+  }
   const int phases = g.transposed ? g.sh * g.sw : 1;
   int64_t maxM;
   if (g.transposed) maxM = (int64_t)g.B * ceil_div(g.Hd, g.sh) * ceil_div(g.Wd, g.sw);
   else maxM = (int64_t)g.B * g.Hd * g.Wd;
   const int bn = pick_bn(g.Cd);
   dim3 grid((unsigned)ceil_div64(maxM, BM), (unsigned)ceil_div(g.Cd, bn), (unsigned)phases);
-  cudaStream_t st = (cudaStream_t)stream;
   switch (bn) {
     case 16: conv_gemm_kernel<16><<<grid, NTHREADS, 0, st>>>(a); break;
     case 32: conv_gemm_kernel<32><<<grid, NTHREADS, 0, st>>>(a); break;

@@ -93,6 +93,28 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The MMA-issuing thread is instruction-bound at N <= 64 (a 128 x 64 x 8 TF32 MMA occupies the tensor pipe for only
+// 32 cycles), so descriptors are built from a per-stage low word plus compile-time offsets: the high word
+// (SBO, version, layout) is an immediate, the low word (start >> 4 | LBO << 16) advances by plain 32-bit adds.
+constexpr uint32_t DESC_HI_K = 64u | (1u << 14) | (2u << 29);             // K-major SWIZZLE_128B, SBO = 1024 B
+constexpr uint32_t DESC_HI_MN = (512u >> 4) | (1u << 14) | (1u << 29);    // MN-major SWIZZLE_128B_BASE32B, SBO = 512 B
+__device__ __forceinline__ uint32_t desc_lo_k(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFF) >> 4) | ((4096u >> 4) << 16);
+}
+template <uint32_t HI>
+__device__ __forceinline__ void umma_tf32_lo(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "n"(HI)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -169,7 +191,7 @@ constexpr int UMF_THREADS = UMF_PRODUCERS + 32;  // + the MMA warp
 constexpr int UM_MAX_PHASE_TAPS = 256;
 
 template <int BN, bool SPLIT, int STAGES, int XFC, bool TRANSPOSED>
-__global__ void __launch_bounds__(UMF_THREADS, 1) conv_umma_kernel(const UmmaArgs a) {
+__global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_kernel(const UmmaArgs a) {
   const msmc_conv_geom& g = a.g;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: A stages (16 KB per plane), B stages (BN*128 B per plane), barriers, tmem slot
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_umma_kernel(const UmmaArg
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform -> uniform register
 
   if (warp < MMA_WARP) {
     // ================================= A producers =================================
@@ -467,22 +489,24 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_umma_kernel(const UmmaArg
     if ((tid & 31) == 0) {
       int s = 0;
       uint32_t ph = 0;
+      const uint32_t a_desc0 = desc_lo_k(smem_u32(sA)), b_desc0 = desc_lo_k(smem_u32(sB));
       for (int ks = 0; ks < n_k; ++ks) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
-        const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+        const uint32_t ad = a_desc0 + (uint32_t)s * (A_BYTES >> 4);
+        const uint32_t bd = b_desc0 + (uint32_t)s * (B_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < UM_BK / 8; ++k) {
-          // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row
-          const uint64_t a_hi = make_desc(a_addr + k * 32), b_hi = make_desc(b_addr + k * 32);
+          // advance 8 tf32 = 32 bytes (2 descriptor units) along K inside the 128-byte swizzle row
+          const uint32_t a_hi = ad + 2 * k, b_hi = bd + 2 * k;
+          const uint32_t acc = (ks > 0 || k > 0) ? 1u : 0u;
           if (SPLIT) {
-            const uint64_t a_lo = make_desc(a_addr + A_PLANE + k * 32), b_lo = make_desc(b_addr + B_PLANE + k * 32);
-            umma_tf32(tmem_base, a_lo, b_hi, IDESC, (ks > 0 || k > 0) ? 1u : 0u);   // small terms first
-            umma_tf32(tmem_base, a_hi, b_lo, IDESC, 1u);
-            umma_tf32(tmem_base, a_hi, b_hi, IDESC, 1u);
+            const uint32_t a_lo = a_hi + (A_PLANE >> 4), b_lo = b_hi + (B_PLANE >> 4);
+            umma_tf32_lo<DESC_HI_K>(tmem_base, a_lo, b_hi, IDESC, acc);   // small terms first
+            umma_tf32_lo<DESC_HI_K>(tmem_base, a_hi, b_lo, IDESC, 1u);
+            umma_tf32_lo<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, 1u);
           } else {
-            umma_tf32(tmem_base, a_hi, b_hi, IDESC, (ks > 0 || k > 0) ? 1u : 0u);
+            umma_tf32_lo<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, acc);
           }
         }
         umma_commit(&empty_bar[s]);   // frees the stage when these MMAs have read it
@@ -532,15 +556,8 @@ struct ReuseArgs {
   int tap_stride;        // rows between consecutive taps (dh * Ws or dw)
   int n_taps;
   int tiles_per_batch;
-  int base_off_mode;     // bring-up switch: 0 = descriptor base offset left 0, 1 = (addr >> 7) & 7
 };
 
-__device__ __forceinline__ uint64_t make_desc_off(uint32_t smem_addr, int mode) {
-  // K-major SWIZZLE_128B descriptor whose start is not 1024-byte aligned
-  uint64_t d = make_desc(smem_addr);
-  if (mode == 1) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
-  return d;
-}
 
 template <int BN, bool SPLIT, int NA, int NBS, int XFC>
 __global__ void __launch_bounds__(RU_THREADS, 1) conv_umma_reuse_kernel(const ReuseArgs a) {
@@ -585,7 +602,7 @@ __global__ void __launch_bounds__(RU_THREADS, 1) conv_umma_reuse_kernel(const Re
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform -> uniform register
 
   if (warp < MMA_WARP) {
     // ================================= operand producers =================================
@@ -712,26 +729,28 @@ __global__ void __launch_bounds__(RU_THREADS, 1) conv_umma_reuse_kernel(const Re
     if ((tid & 31) == 0) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      const uint32_t a_desc0 = desc_lo_k(smem_u32(sA)), b_desc0 = desc_lo_k(smem_u32(sB));
       for (int kc = 0; kc < KC; ++kc) {
         mbar_wait(&fa[sa], pa);
-        const uint32_t a_base = smem_u32(sA + sa * A_BYTES);
-        for (int t = 0; t < T; ++t) {
+        // tap = row shift of the staged tile: the descriptor start moves by tap_stride rows of 128 B (8 units); the
+        // swizzle is a function of the absolute shared-memory address, so the base-offset field stays 0
+        uint32_t ad = a_desc0 + (uint32_t)sa * (A_BYTES >> 4);
+        const uint32_t a_step = (uint32_t)a.tap_stride * 8u;
+        for (int t = 0; t < T; ++t, ad += a_step) {
           mbar_wait(&fb[sb], pb);
           tc_fence_after();
-          const uint32_t a_addr = a_base + (uint32_t)(t * a.tap_stride) * 128u;   // tap = row shift of the staged tile
-          const uint32_t b_addr = smem_u32(sB + sb * B_BYTES);
+          const uint32_t bd = b_desc0 + (uint32_t)sb * (B_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < UM_BK / 8; ++k) {
-            const uint64_t a_hi = make_desc_off(a_addr + k * 32, a.base_off_mode), b_hi = make_desc(b_addr + k * 32);
+            const uint32_t a_hi = ad + 2 * k, b_hi = bd + 2 * k;
             const uint32_t acc = (kc > 0 || t > 0 || k > 0) ? 1u : 0u;
             if (SPLIT) {
-              const uint64_t a_lo = make_desc_off(a_addr + A_PLANE + k * 32, a.base_off_mode),
-                             b_lo = make_desc(b_addr + B_PLANE + k * 32);
-              umma_tf32(tmem_base, a_lo, b_hi, IDESC, acc);
-              umma_tf32(tmem_base, a_hi, b_lo, IDESC, 1u);
-              umma_tf32(tmem_base, a_hi, b_hi, IDESC, 1u);
+              const uint32_t a_lo = a_hi + (A_PLANE >> 4), b_lo = b_hi + (B_PLANE >> 4);
+              umma_tf32_lo<DESC_HI_K>(tmem_base, a_lo, b_hi, IDESC, acc);
+              umma_tf32_lo<DESC_HI_K>(tmem_base, a_hi, b_lo, IDESC, 1u);
+              umma_tf32_lo<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, 1u);
             } else {
-              umma_tf32(tmem_base, a_hi, b_hi, IDESC, acc);
+              umma_tf32_lo<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, acc);
             }
           }
           umma_commit(&eb[sb]);
@@ -879,7 +898,7 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform -> uniform register
 
   if (warp < MMA_WARP) {
     // =============== producers: warps 0-3 stage the source operand, warps 4-7 the output-gradient operand ===============
@@ -1061,27 +1080,30 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
     if ((tid & 31) == 0) {
       int s = 0;
       uint32_t ph = 0;
+      const uint32_t a_desc0 = KMAJOR ? desc_lo_k(smem_u32(sA)) : desc_lo_mn(smem_u32(sA));
+      const uint32_t b_desc0 = KMAJOR ? desc_lo_k(smem_u32(sB)) : desc_lo_mn(smem_u32(sB));
       for (int ks = 0; ks < n_k; ++ks) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
-        const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+        const uint32_t ad = a_desc0 + (uint32_t)s * (A_BYTES >> 4);
+        const uint32_t bd = b_desc0 + (uint32_t)s * (B_BYTES >> 4);
+        if (a.dry != 2) {
 #pragma unroll
-        for (int kg = 0; kg < 4 && a.dry != 2; ++kg) {
-          // one MMA = 8 positions: MN-major -> two 4-row atoms (1 KB) per 32-channel block;
-          //                        K-major  -> 32 bytes further along every 128-byte channel row
-          const uint64_t a_hi = KMAJOR ? make_desc(a_addr + kg * 32) : make_desc_mn(a_addr + kg * 1024);
-          const uint64_t b_hi = KMAJOR ? make_desc(b_addr + kg * 32) : make_desc_mn(b_addr + kg * 1024);
-          if (SPLIT) {
-            const uint64_t a_lo = KMAJOR ? make_desc(a_addr + A_PLANE + kg * 32)
-                                         : make_desc_mn(a_addr + A_PLANE + kg * 1024);
-            const uint64_t b_lo = KMAJOR ? make_desc(b_addr + B_PLANE + kg * 32)
-                                         : make_desc_mn(b_addr + B_PLANE + kg * 1024);
-            umma_tf32(tmem_base, a_lo, b_hi, IDESC, (ks > 0 || kg > 0) ? 1u : 0u);
-            umma_tf32(tmem_base, a_hi, b_lo, IDESC, 1u);
-            umma_tf32(tmem_base, a_hi, b_hi, IDESC, 1u);
-          } else {
-            umma_tf32(tmem_base, a_hi, b_hi, IDESC, (ks > 0 || kg > 0) ? 1u : 0u);
+          for (int kg = 0; kg < 4; ++kg) {
+            // one MMA = 8 positions: MN-major -> two 4-row atoms (1 KB = 64 units) per 32-channel block;
+            //                        K-major  -> 32 bytes (2 units) further along every 128-byte channel row
+            constexpr uint32_t KSTEP = KMAJOR ? 2u : 64u;
+            constexpr uint32_t HI = KMAJOR ? DESC_HI_K : DESC_HI_MN;
+            const uint32_t a_hi = ad + kg * KSTEP, b_hi = bd + kg * KSTEP;
+            const uint32_t acc = (ks > 0 || kg > 0) ? 1u : 0u;
+            if (SPLIT) {
+              const uint32_t a_lo = a_hi + (A_PLANE >> 4), b_lo = b_hi + (B_PLANE >> 4);
+              umma_tf32_lo<HI>(tmem_base, a_lo, b_hi, IDESC, acc);
+              umma_tf32_lo<HI>(tmem_base, a_hi, b_lo, IDESC, 1u);
+              umma_tf32_lo<HI>(tmem_base, a_hi, b_hi, IDESC, 1u);
+            } else {
+              umma_tf32_lo<HI>(tmem_base, a_hi, b_hi, IDESC, acc);
+            }
           }
         }
         umma_commit(&empty_bar[s]);
@@ -1229,7 +1251,10 @@ extern "C" int msmc_conv_forward_umma(const msmc_conv_geom* gp, const float* src
   // short reduction loops (the M-heavy, few-channel layers) are dominated by per-CTA prologue / epilogue latency:
   // a 2-stage ring halves the shared-memory footprint so two CTAs share an SM and overlap those phases
   const int n_k_est = g.KH * g.KW * (g.Cs / UM_BK) / (g.transposed ? g.sh * g.sw : 1);
-  const bool shallow = n_k_est <= 24;
+  // measured on the full train step: two co-resident CTAs with 2-stage rings beat one CTA with a 4-stage ring for
+  // every BN <= 64 shape (114.5 -> 111.5 ms/step), so "shallow" is the default; MSMC_UMMA_SHALLOW=2 restores the deep ring
+  static const int shallow_mode = [] { const char* e = getenv("MSMC_UMMA_SHALLOW"); return e ? atoi(e) : 1; }();
+  const bool shallow = shallow_mode == 1 ? true : (shallow_mode == 2 ? false : n_k_est <= 24);
   if (split) {
     switch (bn) {
       case 32: if (shallow) LAUNCH_UMMA(32, true, 2); else LAUNCH_UMMA(32, true, 4); break;   // 2 or 4 x 40 KB
@@ -1384,10 +1409,6 @@ extern "C" int msmc_conv_forward_umma_reuse(const msmc_conv_geom* gp, const floa
   a.dst_aux = dst_aux; a.dst = dst;
   a.Ls = g.Hs * g.Ws; a.Ld = g.Hd * g.Wd;
   a.tiles_per_batch = ceil_div(a.Ld, UM_BM);
-  {
-    const char* e = getenv("MSMC_REUSE_BASEOFF");
-    a.base_off_mode = e ? atoi(e) : 0;
-  }
   dim3 grid((unsigned)(a.tiles_per_batch * g.B), (unsigned)ceil_div(g.Cd, BN));
   cudaStream_t st = (cudaStream_t)stream;
   const int xfc = g.src_xf == MSMC_XF_NONE ? XFC_NONE

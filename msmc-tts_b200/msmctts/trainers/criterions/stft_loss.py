@@ -45,16 +45,22 @@ class MelLoss(nn.Module):
         basis, self.left, self.n_freq_pad = dft_basis(fft_size, win_size, normalized=False)
         self.register_buffer("basis", basis, persistent=False)
         self.register_buffer("basis_t", basis[:win_size].t().contiguous(), persistent=False)
-        self.register_buffer("mel_basis", mel_filterbank_slaney(sample_rate, fft_size, num_mels, 0,
-                                                                sample_rate // 2), persistent=False)
+        mel_basis = mel_filterbank_slaney(sample_rate, fft_size, num_mels, 0, sample_rate // 2)   # (num_mels, F)
+        self.register_buffer("mel_basis", mel_basis, persistent=False)
+        # GEMM layout (Fp, num_mels), rows past F zero: padded magnitude x filterbank on the tensor cores
+        mel_g = torch.zeros(self.n_freq_pad, num_mels)
+        mel_g[:self.n_freq] = mel_basis.t()
+        self.register_buffer("mel_basis_g", mel_g, persistent=False)
 
     def mel_spectrogram(self, y):
         """y (B, L) -> log-mel (B, frames, num_mels)"""
         B, L = y.shape
         pad = int((self.fft_size - self.hop_size) / 2) - self.left
         spec = Fn.stft_frames(y, self.basis, self.basis_t, self.hop_size, pad, self.win_size)
-        mag = Fn.spec_magnitude(spec, 1e-9, True, self.n_freq)
-        mel = Fn.linear_cl(mag, self.mel_basis)
+        mag = Fn.spec_magnitude(spec, 1e-9, True)                       # (B, frames, Fp), pad columns meet zero weights
+        Bf, Tf, Fp = mag.shape
+        mel = Fn.conv_cl(mag.reshape(Bf * Tf, 1, 1, Fp), self.mel_basis_g,
+                         out_channels=self.num_mels).reshape(Bf, Tf, self.num_mels)
         return Fn.log_clamp(mel, 1e-5)
 
     def forward(self, predicts, targets):

@@ -32,12 +32,12 @@ def create_fb_matrix(n_freqs, f_min, f_max, n_mels, sample_rate, norm=None):
 
 def dft_basis(n_fft, win_length, normalized, dtype=torch.float32):
     """(win_length, 2*Fp) basis [cos | 0 | -sin | 0] * hann(win_length), for the window's non-zero span only; each
-    half is zero-padded from F = n_fft/2+1 to Fp = a multiple of 16 so the spectrum has 32k channels (tensor-core
+    half is zero-padded from F = n_fft/2+1 to Fp = a multiple of 32 so spectrum and magnitude are tensor-core
     GEMM eligibility).  torch.stft centres a short window inside n_fft (left pad (n_fft - win)/2).
     Returns (basis, left, Fp)."""
     left = (n_fft - win_length) // 2
     F = n_fft // 2 + 1
-    Fp = (F + 15) // 16 * 16
+    Fp = (F + 31) // 32 * 32
     k = np.arange(win_length, dtype=np.float64) + left
     f = np.arange(F, dtype=np.float64)
     ang = 2.0 * np.pi * np.outer(k, f) / n_fft
@@ -58,12 +58,19 @@ class MelScale(nn.Module):
         self.f_min = f_min
         fb = create_fb_matrix(n_stft, self.f_min, self.f_max, n_mels, sample_rate) if n_stft else torch.empty(0)
         self.register_buffer("fb", fb, persistent=False)
+        # rows zero-padded to the padded spectrum width: the magnitude keeps its 32-aligned pitch and the filterbank
+        # product is a tensor-core GEMM (pad columns of the magnitude meet zero weights)
+        n_pad = (fb.shape[0] + 31) // 32 * 32 if n_stft else 0
+        fb_p = torch.zeros(n_pad, n_mels)
+        if n_stft:
+            fb_p[:fb.shape[0]] = fb
+        self.register_buffer("fb_p", fb_p, persistent=False)
 
     def forward_cl(self, mag):
-        """mag (B, frames, F) -> (B, frames, n_mels)"""
+        """mag (B, frames, F | Fp) -> (B, frames, n_mels)"""
         B, T, Fq = mag.shape
-        y = Fn.conv_cl(mag.reshape(B * T, 1, 1, Fq), self.fb, wstr=(0, 0, self.n_mels, 1),
-                       out_channels=self.n_mels)
+        fb = self.fb_p if Fq == self.fb_p.shape[0] else self.fb
+        y = Fn.conv_cl(mag.reshape(B * T, 1, 1, Fq), fb, out_channels=self.n_mels)
         return y.reshape(B, T, self.n_mels)
 
 
@@ -89,9 +96,10 @@ class TorchSTFT(nn.Module):
 
     def transform_cl(self, x):
         """x (B, L) -> (B, frames, F, C) with C = 2 ('double': lin, log), else 1"""
-        mag = Fn.spec_magnitude(self.spectrum_cl(x), 1e-7, False, self.n_freq)
         if self.mel_scale is not None:
-            mag = self.mel_scale.forward_cl(mag)
+            mag = self.mel_scale.forward_cl(Fn.spec_magnitude(self.spectrum_cl(x), 1e-7, False))   # padded width
+        else:
+            mag = Fn.spec_magnitude(self.spectrum_cl(x), 1e-7, False, self.n_freq)
         if self.domain == "double":
             return Fn.mel_double(mag, self.ref_level_db, self.min_level_db)
         if self.domain == "linear":
