@@ -326,9 +326,8 @@ __global__ void __launch_bounds__(DS_THREADS) conv_direct_small_kernel(const Con
       const float* sp = a.src + off * g.ld_src;
       const float* ap = need_aux ? a.src_aux + off * g.ld_saux : nullptr;
       const float* wt = s_w + (kh * g.KW + kw) * g.Cs * CDP;
-      for (int c = 0; c < g.Cs; ++c) {
-        float v = __ldg(sp + c);
-        if (g.src_xf != MSMC_XF_NONE) v = apply_xf(g.src_xf, g.src_slope, v, need_aux ? __ldg(ap + c) : 0.f);
+      auto mac = [&](float v, float aux, int c) {
+        if (g.src_xf != MSMC_XF_NONE) v = apply_xf(g.src_xf, g.src_slope, v, aux);
         const float4* w4 = reinterpret_cast<const float4*>(wt + c * CDP);
 #pragma unroll
         for (int j = 0; j < CDP / 4; ++j) {
@@ -338,6 +337,16 @@ __global__ void __launch_bounds__(DS_THREADS) conv_direct_small_kernel(const Con
           acc[4 * j + 2] = fmaf(v, w.z, acc[4 * j + 2]);
           acc[4 * j + 3] = fmaf(v, w.w, acc[4 * j + 3]);
         }
+      };
+      if (a.vec_src) {          // Cs % 4 == 0 here, 16-byte aligned rows
+        for (int c = 0; c < g.Cs; c += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(sp + c));
+          float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (need_aux) u = __ldg(reinterpret_cast<const float4*>(ap + c));
+          mac(v.x, u.x, c); mac(v.y, u.y, c + 1); mac(v.z, u.z, c + 2); mac(v.w, u.w, c + 3);
+        }
+      } else {
+        for (int c = 0; c < g.Cs; ++c) mac(__ldg(sp + c), need_aux ? __ldg(ap + c) : 0.f, c);
       }
     }
   const bool dneed_aux = xf_needs_aux(g.dst_xf);
@@ -872,6 +881,8 @@ extern "C" int msmc_conv_forward(const msmc_conv_geom* gp, const float* src, con
   a.b_kmajor = (g.ws_cd != 1 && g.ws_cs == 1);
   cudaStream_t st = (cudaStream_t)stream;
   if (direct_small_eligible(g)) {
+    a.vec_src = (g.Cs % 4 == 0) && (g.ld_src % 4 == 0) && aligned16(src) &&
+                (!xf_needs_aux(g.src_xf) || ((g.ld_saux % 4 == 0) && aligned16(src_aux)));
     const int64_t Mall = (int64_t)g.B * g.Hd * g.Wd;
     const unsigned blocks = (unsigned)ceil_div64(Mall, DS_THREADS);
     if (g.Cd <= 4) conv_direct_small_kernel<4><<<blocks, DS_THREADS, 0, st>>>(a);

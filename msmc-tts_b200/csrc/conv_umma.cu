@@ -560,7 +560,7 @@ struct ReuseArgs {
 
 
 template <int BN, bool SPLIT, int NA, int NBS, int XFC>
-__global__ void __launch_bounds__(RU_THREADS, 1) conv_umma_reuse_kernel(const ReuseArgs a) {
+__global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse_kernel(const ReuseArgs a) {
   const msmc_conv_geom& g = a.g;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1427,10 +1427,11 @@ extern "C" int msmc_conv_forward_umma_reuse(const msmc_conv_geom* gp, const floa
     else if (xfc == XFC_LRELU) LAUNCH_RU_X(BN_, SPLIT_, NA_, NB_, XFC_LRELU);  \
     else LAUNCH_RU_X(BN_, SPLIT_, NA_, NB_, XFC_GENERIC);                      \
   } while (0)
+  static const int two_ctas = [] { const char* e = getenv("MSMC_REUSE_TWO"); return e ? atoi(e) : 1; }();
   if (split) {
     switch (BN) {
-      case 32: LAUNCH_RU(32, true, 3, 6); break;     // 144 KB + 48 KB
-      case 64: LAUNCH_RU(64, true, 3, 4); break;     // 144 KB + 64 KB
+      case 32: if (two_ctas) LAUNCH_RU(32, true, 1, 6); else LAUNCH_RU(32, true, 3, 6); break;   // 48|144 KB + 48 KB
+      case 64: if (two_ctas) LAUNCH_RU(64, true, 1, 3); else LAUNCH_RU(64, true, 3, 4); break;   // 48|144 KB + 48|64 KB
       default: LAUNCH_RU(128, true, 2, 3); break;    //  96 KB + 96 KB
     }
   } else {

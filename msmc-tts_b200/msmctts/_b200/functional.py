@@ -383,7 +383,8 @@ class _PrepWeightFn(torch.autograd.Function):
     """(v[, g]) -> GEMM-layout weight; weight_norm (dim=0) when g is given."""
 
     @staticmethod
-    def forward(ctx, v, g, O, I, J, so, si, sj, out_shape):
+    def forward(ctx, v, g, O, I, J, so, si, sj, out_shape, token):
+        ctx.token = token
         v = v.contiguous()
         w = torch.empty(out_shape, dtype=torch.float32, device=v.device)
         inv = torch.empty(O, dtype=torch.float32, device=v.device) if g is not None else None
@@ -400,6 +401,8 @@ class _PrepWeightFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gw):
         v, g, inv = ctx.saved_tensors
+        if ctx.token is not None:
+            ctx.token["spent"] = True        # the layer-level cache must not hand this node out again
         O, I, J, so, si, sj = ctx.dims
         gw = gw.contiguous()
         dv = torch.empty_like(v)
@@ -410,10 +413,28 @@ class _PrepWeightFn(torch.autograd.Function):
                L.ptr(inv), L.ptr(dv), L.ptr(dg), O, I, J, meta=meta)
         if ctx.has_g:
             dg = dg.reshape(g.shape)
-        return dv, dg, None, None, None, None, None, None, None
+        return dv, dg, None, None, None, None, None, None, None, None
 
 
-def prep_conv_weight(v, g=None, transposed=False):
+# id of the trainer step in flight (0 = none): layers share one re-parametrised weight per parameter version inside it
+PREP_SCOPE = [0]
+_prep_scope_ids = [0]
+
+
+class prep_scope(object):
+    """`with prep_scope():` -- layers called more than once on unchanged parameters reuse their prepared weight"""
+
+    def __enter__(self):
+        _prep_scope_ids[0] += 1
+        self.prev = PREP_SCOPE[0]
+        PREP_SCOPE[0] = _prep_scope_ids[0]
+
+    def __exit__(self, *exc):
+        PREP_SCOPE[0] = self.prev
+        return False
+
+
+def prep_conv_weight(v, g=None, transposed=False, token=None):
     """torch conv weight -> GEMM layout [KH][KW][Cs][Cd] (contiguous).
     Conv:          v (Co, Ci, KH, KW) or (Co, Ci, K);  weight_norm over (Ci, K...) per Co.
     ConvTranspose: v (Cin, Cout, K);                    weight_norm over (Cout, K) per Cin (torch dim=0)."""
@@ -429,7 +450,7 @@ def prep_conv_weight(v, g=None, transposed=False):
     else:
         # o = cs (Cin), i = cd (Cout): offset = j*(O*I) + o*I + i
         shape, so, si, sj = (KH, KW, O, I), I, 1, O * I
-    return _PrepWeightFn.apply(v, g, O, I, J, so, si, sj, shape)
+    return _PrepWeightFn.apply(v, g, O, I, J, so, si, sj, shape, token)
 
 
 # ------------------------------------------------------------------------------------------------ VQ

@@ -19,6 +19,26 @@ def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 
 
+def _prepped(mod, v, g, transposed=False, swap_taps=False):
+    """GEMM-layout (weight-normalised) weight of `mod`, re-used while the parameters are unchanged.
+
+    The discriminator runs twice per phase (fake, real) on the same weights: the re-parametrisation, its
+    tensor-core operand images and its backward then run once per parameter version instead of once per call.
+    The entry is dropped as soon as a backward pass has consumed it (its saved tensors are gone by then)."""
+    scope = Fn.PREP_SCOPE[0]
+    if scope == 0:       # sharing is only safe inside a trainer step (nobody edits .data behind autograd's back there)
+        return Fn.prep_conv_weight(v.transpose(2, 3) if swap_taps else v, g, transposed=transposed)
+    grad = torch.is_grad_enabled() and (v.requires_grad or (g is not None and g.requires_grad))
+    key = (scope, v._version, -1 if g is None else g._version, grad, v.data_ptr())
+    hit = mod.__dict__.get("_msmc_prep")
+    if hit is not None and hit[0] == key and not hit[2]["spent"]:
+        return hit[1]
+    token = {"spent": False}
+    w = Fn.prep_conv_weight(v.transpose(2, 3) if swap_taps else v, g, transposed=transposed, token=token)
+    mod.__dict__["_msmc_prep"] = (key, w, token)
+    return w
+
+
 class Linear(nn.Linear):
     """nn.Linear parameters; forward = msmc_conv_forward with the weight consumed in its native (Co, Ci) layout."""
 
@@ -45,7 +65,7 @@ class Conv1d(nn.Module):
         v, g = self.gemm_weight()
         if self.kernel_size == 1 and g is None:
             return Fn.linear_cl(x, v, self.bias, residual=residual, post=post, pre_slope=pre_slope)
-        w = Fn.prep_conv_weight(v, g)
+        w = _prepped(self, v, g)
         r4 = residual.unsqueeze(1) if residual is not None else None
         y = Fn.conv_cl(x.unsqueeze(1), w, self.bias, r4, kernel=(1, self.kernel_size), stride=(1, self.stride),
                        dilation=(1, self.dilation), padding=(0, self.padding), pre_slope=pre_slope, post=post)
@@ -79,7 +99,7 @@ class WNConvTranspose1d(nn.Module):
         self.weight_v = nn.Parameter(v)
 
     def forward(self, x, pre_slope=None):
-        w = Fn.prep_conv_weight(self.weight_v, self.weight_g, transposed=True)
+        w = _prepped(self, self.weight_v, self.weight_g, transposed=True)
         y = Fn.conv_cl(x.unsqueeze(1), w, self.bias, kernel=(1, self.kernel_size), stride=(1, self.stride),
                        padding=(0, self.padding), transposed=True, pre_slope=pre_slope)
         return y.squeeze(1)
@@ -103,12 +123,12 @@ class WNConv2d(nn.Module):
     def forward(self, x, pre_slope=None, post="none"):
         KH, KW = self.kernel_size
         if not self.swap_hw:
-            w = Fn.prep_conv_weight(self.weight_v, self.weight_g)   # [kh][kw][ci][co]
+            w = _prepped(self, self.weight_v, self.weight_g)   # [kh][kw][ci][co]
             return Fn.conv_cl(x, w, self.bias, kernel=(KH, KW), stride=self.stride, padding=self.padding,
                               reflect=self.reflect, pre_slope=pre_slope, post=post)
         # exchanged spatial axes: transpose the taps, then the standard contiguous GEMM layout [kw][kh][ci][co]
         # (the weight norm runs over (ci, kh, kw), so it is unaffected by the permutation)
-        w = Fn.prep_conv_weight(self.weight_v.transpose(2, 3), self.weight_g)
+        w = _prepped(self, self.weight_v, self.weight_g, swap_taps=True)
         return Fn.conv_cl(x, w, self.bias, kernel=(KW, KH), stride=self.stride[::-1], padding=self.padding[::-1],
                           reflect=self.reflect, pre_slope=pre_slope, post=post)
 

@@ -35,12 +35,16 @@ class BaseTrainer(object):
         self.optimizer = build_optimizer(self.model, self.config.optimizer)
         return self.optimizer
 
-    def backward(self, loss, module_name):
-        """backward + (when data-parallel) the bucketed, overlapped all-reduce of that sub-module's gradients"""
+    def backward(self, loss, module_name, inputs=None):
+        """backward + (when data-parallel) the bucketed, overlapped all-reduce of that sub-module's gradients;
+        `inputs` restricts the pass to those leaves (gradients of anything else are neither computed nor stored)"""
         reducer = getattr(self.model, "grad_reducers", {}).get(module_name) if self.distributed else None
         if reducer is not None:
             reducer.arm()
-        loss.backward()
+        if inputs is None:
+            loss.backward()
+        else:
+            loss.backward(inputs=[p for p in inputs if p.requires_grad])
         if reducer is not None:
             reducer.finish()
 

@@ -62,8 +62,19 @@ class QuantizerLoss(nn.Module):
 class VQGANTrainer(BaseTrainer):
     def __init__(self, config, model, num_gpus=1, rank=0, warmup_steps=0, lambda_frame=1.0,
                  eval_inteval_iters=1000, grad_clip_thresh=1.0, sample_lengths=24000, lambda_vq=1, lambda_pr=1,
-                 lambda_fm=2, lambda_stft=45, stft_loss_func="mel_loss", stft_loss_config=None, cuda_graph=False):
+                 lambda_fm=2, lambda_stft=45, stft_loss_func="mel_loss", stft_loss_config=None, cuda_graph=False,
+                 reference_schedule=False):
         super().__init__(config, model, num_gpus, rank)
+        # reference_schedule=False (default) keeps every loss value and every parameter update of the reference's
+        # step but drops work whose result the reference discards:
+        #   * the discriminator step scores cat(fake, real) in ONE pass (no batch statistics anywhere in D, so the
+        #     per-sample math is unchanged; the two weight-gradient sums become one);
+        #   * the generator step back-propagates only into the autoencoder: the reference also fills D's .grad
+        #     there (msmctts_trainer.py:182-207) and zeroes it before it is ever read (:166), and the real branch of
+        #     the feature-matching pass needs no graph at all.
+        # reference_schedule=True replays the reference's exact launch schedule (4 separate D passes, D gradients
+        # computed in the G step).
+        self.reference_schedule = bool(reference_schedule)
         # cuda_graph=True: the sync-free step body is captured once per (shape, phase) into a CUDA graph and
         # replayed -- ~2.6k kernel launches and all Python/autograd dispatch collapse into one graph launch
         self.use_cuda_graph = bool(cuda_graph)
@@ -146,6 +157,13 @@ class VQGANTrainer(BaseTrainer):
         return st["out"]
 
     def _step(self, mel, mel_length, wav, starts, warmup, gan):
+        if mel.is_cuda:
+            from msmctts._b200.functional import prep_scope
+            with prep_scope():
+                return self._step_body(mel, mel_length, wav, starts, warmup, gan)
+        return self._step_body(mel, mel_length, wav, starts, warmup, gan)
+
+    def _step_body(self, mel, mel_length, wav, starts, warmup, gan):
         """sync-free body; everything inside is device work (graph-capturable)"""
         losses = {}
         ae, disc = self.model.autoencoder, getattr(self.model, "discriminator", None)
@@ -173,8 +191,13 @@ class VQGANTrainer(BaseTrainer):
             losses["stft_loss"] = stft_loss
             g_loss = g_loss + self.lambda_stft * stft_loss
             # ---- discriminator step (reference :162-179)
-            fake_scores, _ = disc(predict.detach())
-            real_scores, _ = disc(target)
+            if self.reference_schedule:
+                fake_scores, _ = disc(predict.detach())
+                real_scores, _ = disc(target)
+            else:
+                nb = predict.shape[0]
+                both, _ = disc(torch.cat([predict.detach(), target], dim=0))
+                fake_scores, real_scores = [s[:nb] for s in both], [s[nb:] for s in both]
             d_real = sum(F.mse_loss(s, torch.ones_like(s)) for s in real_scores)
             d_fake = sum(F.mse_loss(s, torch.zeros_like(s)) for s in fake_scores)
             d_loss = d_real + d_fake
@@ -184,7 +207,11 @@ class VQGANTrainer(BaseTrainer):
             self.optimizer.step(["discriminator"])
             # ---- generator step (reference :182-201): D has already been updated, both passes are recomputed
             fake_scores, fake_feats = disc(predict)
-            _, real_feats = disc(target)
+            if self.reference_schedule:
+                _, real_feats = disc(target)
+            else:
+                with torch.no_grad():
+                    _, real_feats = disc(target)
             adv = sum(F.mse_loss(s, torch.ones_like(s)) for s in fake_scores)
             fm = sum(F.l1_loss(a, b) for fa, fb in zip(fake_feats, real_feats) for a, b in zip(fa, fb))
             scale = self.lambda_fm if self.lambda_fm != "auto" else (g_loss / fm).detach()
@@ -192,7 +219,8 @@ class VQGANTrainer(BaseTrainer):
             g_loss = g_loss + adv_loss
             losses.update(fm_loss=fm, adv_loss=adv_loss, g_loss=g_loss)
         self.optimizer.zero_grad(["autoencoder"])
-        self.backward(g_loss, "autoencoder")
+        only = None if (self.reference_schedule or not gan) else list(self.model.autoencoder.parameters())
+        self.backward(g_loss, "autoencoder", inputs=only)
         nn.utils.clip_grad_norm_(self.model.autoencoder.parameters(), self.grad_clip_thresh)
         self.optimizer.step(["autoencoder"])
         return {"loss": {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}}
