@@ -203,7 +203,7 @@ def workload_config(n):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def build_gpu_trainer(cfg, device, distributed, rank, world, use_graph=False):
+def build_gpu_trainer(cfg, device, distributed, rank, world, use_graph=False, reference_schedule=False):
     from msmctts.tasks.msmc_tts import MSMCTTS
     from msmctts.trainers.msmctts_trainer import VQGANTrainer
     from msmctts.utils.config import Config
@@ -221,6 +221,7 @@ def build_gpu_trainer(cfg, device, distributed, rank, world, use_graph=False):
     kwargs.pop("_name")
     kwargs["warmup_steps"] = 0      # bench the post-warm-up (GAN) step
     kwargs["cuda_graph"] = use_graph
+    kwargs["reference_schedule"] = reference_schedule
     trainer = VQGANTrainer(config, task, num_gpus=world, rank=rank, **kwargs)
     trainer.build_optimizer()
     task.train()
@@ -276,7 +277,8 @@ def run_b200(args, rank, world, local_rank):
     if distributed and not dist.is_initialized():
         dist.init_process_group("nccl")
     cfg = load_cfg()
-    trainer = build_gpu_trainer(cfg, device, distributed, rank, world, use_graph=not args.no_graph)
+    trainer = build_gpu_trainer(cfg, device, distributed, rank, world, use_graph=not args.no_graph,
+                                reference_schedule=args.reference_schedule)
     pk = peaks()
     fixed_win = [(100, 100 + WIN_FRAMES)] * B_PER_GPU
     dev_batch = synth_batch(B_PER_GPU, 1000 + rank, device=device)
@@ -388,7 +390,12 @@ def run_b200(args, rank, world, local_rank):
             "metric": "mel-frames/sec MSMC-VQ-GAN train step", "value": value, "unit": "mel-frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world), "clocks": clocks,
+            "config": dict(workload_config(world), schedule=(
+                "reference (4 separate D passes, D gradients computed and discarded in the G step)"
+                if args.reference_schedule else
+                "same losses and parameter updates as the reference; D step scores cat(fake, real) in one pass, G "
+                "step back-propagates only into the autoencoder (the reference zeroes D's G-step gradients unread); "
+                "--reference-schedule replays the reference's launches")), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "mel-frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
@@ -407,6 +414,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as a CUDA graph")
+    ap.add_argument("--reference-schedule", action="store_true",
+                    help="replay the reference's launch schedule: 4 separate discriminator passes and discriminator "
+                         "gradients computed (then discarded) in the generator step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -24,13 +24,15 @@ def _no_dropout(model):
             mod.dropout = 0.0
 
 
-def test_two_train_steps_vs_oracle():
+@pytest.mark.parametrize("reference_schedule", [False, True], ids=["fused-schedule", "reference-schedule"])
+def test_two_train_steps_vs_oracle(reference_schedule):
+    """both launch schedules (see VQGANTrainer.__init__) must reproduce the reference's losses and updates"""
     import bench
     from oracle.train_step import OracleTrainer
     cfg = bench.load_cfg()
     cfg["autoencoder"]["quantizer_config"]["embedding_sizes"] = 64
     dev = torch.device("cuda:0")
-    trainer = bench.build_gpu_trainer(cfg, dev, False, 0, 1)
+    trainer = bench.build_gpu_trainer(cfg, dev, False, 0, 1, reference_schedule=reference_schedule)
     _no_dropout(trainer.model)
     sd_ae = {k: v.detach().cpu().clone() for k, v in trainer.model.autoencoder.state_dict().items()}
     sd_d = {k: v.detach().cpu().clone() for k, v in trainer.model.discriminator.state_dict().items()}
