@@ -1121,6 +1121,284 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Weight gradient of stride-1 convolutions with TAP REUSE.
+//
+// dW[tap][cs][cd] = sum_p src[p + tap*d - pad][cs] * gout[p][cd]: every tap reads the SAME source rows, shifted by
+// tap*d positions.  In the MN-major operand layout a shared-memory row is one position, so
+//   * the K extent (positions) of a tap starts `tap*d` rows further down the staged tile, and
+//   * the four 32-lane M blocks of one tcgen05.mma are addressed through the descriptor's leading-dimension byte
+//     offset (LBO).  Setting LBO = d*128 B makes the four M blocks FOUR CONSECUTIVE TAPS of one 32-channel block:
+//     one MMA accumulates dW[4 taps][32 channels][BN] from a single staged copy of the source rows.
+// The source tile (32 positions + tap reach) is therefore staged once per stage instead of once per tap and
+// per row-block CTA (11 x fewer operand bytes on the k=11 MRF convs) and one CTA owns every tap of its channel
+// blocks: accumulator group (cb, tap-group) lives in its own BN-column slice of TMEM (<= 512 columns).
+//   applies to: forward-form stride-1 convs with a 1-D tap pattern in flattened position space (same rule as the
+//   forward tap-reuse kernel), Cs % 32 == 0, Cd % 32 == 0, 3 <= taps, 32 + (4*ceil(taps/4) - 1) * d <= 96 rows.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int WR_POS = 32;                 // positions (K) per stage
+constexpr int WR_ROWS = 96;                // staged source rows per stage (32 + tap reach)
+constexpr int WR_MAX_STAGES = 4;
+constexpr int WR_A_CB = WR_ROWS * 128;     // bytes of one 32-channel block of the source tile (12 KB, 1 KB aligned)
+
+struct WgradReuseArgs {
+  msmc_conv_geom g;
+  const float* src;
+  const float* src_aux;
+  const float* gout;
+  const float* gout_aux;
+  float* partial;          // [splits][Ktot*Cd + Cd]
+  int Ls, Ld;              // positions per batch element (source / output)
+  int pad_rows, tap_stride, n_taps;
+  int kc_cta;              // 32-channel source blocks per CTA (1 or 2)
+  int stages_per_batch;    // ceil(Ld / 32)
+  int total_stages;        // B * stages_per_batch
+  int stages_per_split;
+  int n_stages;            // shared-memory ring depth (2..4)
+  int want_bias;
+};
+
+template <int BN, bool SPLIT, int XFC>
+__global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_reuse_kernel(const WgradReuseArgs a) {
+  const msmc_conv_geom& g = a.g;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NP = SPLIT ? 2 : 1;
+  constexpr int NB = BN / 32;
+  constexpr int B_PLANE = NB * 4096;
+  const int KCC = a.kc_cta;
+  const int A_PLANE = KCC * WR_A_CB;
+  const int A_BYTES = NP * A_PLANE;
+  constexpr int B_BYTES = NP * B_PLANE;
+  const int NS = a.n_stages;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + NS * A_BYTES;
+  float* s_bias = reinterpret_cast<float*>(sB + NS * B_BYTES);          // [32][BN] column-sum staging
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + 32 * BN);
+  uint64_t* empty_bar = full_bar + WR_MAX_STAGES;
+  uint64_t* accum_bar = empty_bar + WR_MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = a.n_taps;
+  const int TG = (T + 3) >> 2;                         // tap groups of 4
+  const int d = a.tap_stride;
+  const int r_in = WR_POS + (4 * TG - 1) * d;          // staged rows (<= WR_ROWS)
+  const int cb0 = blockIdx.x * KCC;                    // first 32-channel source block of this CTA
+  const int n0 = blockIdx.y * BN;
+  const int s_beg = blockIdx.z * a.stages_per_split;
+  const int s_end = min(a.total_stages, s_beg + a.stages_per_split);
+  const int n_k = s_end - s_beg;                       // >= 1 by construction
+  const int groups = KCC * TG;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < groups * BN) tmem_cols <<= 1;
+  constexpr int MMA_WARP = UMF_PRODUCERS / 32;
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], UMF_PRODUCERS / 32);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
+  float* part = a.partial + (int64_t)blockIdx.z * (Ktot * g.Cd + g.Cd);
+
+  if (warp < MMA_WARP) {
+    // ======================= producers: one 16-byte chunk of rows rsub, rsub + 32, rsub + 64 =======================
+    const int chunk = tid & 7;
+    const int rsub = tid >> 3;                          // 0..31
+    constexpr bool NEED_AUX = (XFC == XFC_GENERIC);
+    const bool need_aux = NEED_AUX && xf_needs_aux(g.src_xf);
+    const bool gneed_aux = xf_needs_aux(g.dst_xf);
+    const bool do_bias = a.want_bias && blockIdx.x == 0;
+    float4 va[6], ua[6], vb[NB], ub[NB];
+    float bsum[NB][4];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) bsum[j][0] = bsum[j][1] = bsum[j][2] = bsum[j][3] = 0.f;
+    int bidx = s_beg / a.stages_per_batch;              // batch element / first position of the next stage to gather
+    int l0 = (s_beg - bidx * a.stages_per_batch) * WR_POS;
+
+    auto gather = [&]() {
+      const int64_t pix0 = (int64_t)bidx * a.Ls;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int r = rsub + 32 * i;
+          const int p = l0 - a.pad_rows + r;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f), u = v;
+          if (c < KCC && r < r_in && (unsigned)p < (unsigned)a.Ls) {
+            const int coff = (cb0 + c) * 32 + chunk * 4;
+            v = __ldg(reinterpret_cast<const float4*>(a.src + (pix0 + p) * g.ld_src + coff));
+            if (NEED_AUX && need_aux)
+              u = __ldg(reinterpret_cast<const float4*>(a.src_aux + (pix0 + p) * g.ld_saux + coff));
+          }
+          va[c * 3 + i] = v;
+          if (NEED_AUX) ua[c * 3 + i] = u;
+        }
+      }
+      const int lo = l0 + rsub;
+      const int64_t m = (int64_t)bidx * a.Ld + lo;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f), u = v;
+        if (lo < a.Ld) {
+          v = __ldg(reinterpret_cast<const float4*>(a.gout + m * g.ld_dst + n0 + j * 32 + chunk * 4));
+          if (gneed_aux) u = __ldg(reinterpret_cast<const float4*>(a.gout_aux + m * g.ld_daux + n0 + j * 32 + chunk * 4));
+        }
+        vb[j] = v;
+        ub[j] = u;
+      }
+      l0 += WR_POS;
+      if (l0 >= a.stages_per_batch * WR_POS) { l0 = 0; ++bidx; }
+    };
+
+    gather();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int ks = 0; ks < n_k; ++ks) {
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      uint8_t* abase = sA + s * A_BYTES;
+      uint8_t* bbase = sB + s * B_BYTES;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int r = rsub + 32 * i;
+          if (c < KCC && r < r_in) {
+            const float4 x = xf4<XFC>(g, va[c * 3 + i], NEED_AUX ? ua[c * 3 + i] : make_float4(0.f, 0.f, 0.f, 0.f));
+            uint8_t* dp = abase + c * WR_A_CB + mn_off(r, chunk);
+            if (SPLIT) {
+              const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+              *reinterpret_cast<float4*>(dp) = hi;
+              *reinterpret_cast<float4*>(dp + A_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+            } else {
+              *reinterpret_cast<float4*>(dp) = x;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        float4 x = vb[j];
+        if (g.dst_xf != MSMC_XF_NONE) {
+          x.x = apply_xf(g.dst_xf, g.dst_slope, x.x, ub[j].x); x.y = apply_xf(g.dst_xf, g.dst_slope, x.y, ub[j].y);
+          x.z = apply_xf(g.dst_xf, g.dst_slope, x.z, ub[j].z); x.w = apply_xf(g.dst_xf, g.dst_slope, x.w, ub[j].w);
+        }
+        bsum[j][0] += x.x; bsum[j][1] += x.y; bsum[j][2] += x.z; bsum[j][3] += x.w;
+        uint8_t* dp = bbase + j * 4096 + mn_off(rsub, chunk);
+        if (SPLIT) {
+          const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+          *reinterpret_cast<float4*>(dp) = hi;
+          *reinterpret_cast<float4*>(dp + B_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+        } else {
+          *reinterpret_cast<float4*>(dp) = x;
+        }
+      }
+      if (ks + 1 < n_k) gather();
+      publish_and_arrive_warp(&full_bar[s]);
+      if (++s == NS) { s = 0; ph ^= 1u; }
+    }
+
+    // ================================= epilogue =================================
+    if (do_bias) {
+      // fixed-order column sums: thread (rsub, chunk) parks its 4 x NB partials, 32 x BN floats in total
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s_bias[rsub * BN + j * 32 + chunk * 4 + e] = bsum[j][e];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(UMF_PRODUCERS) : "memory");      // producer warps only
+    if (do_bias && tid < BN) {
+      float t = 0.f;
+      for (int r = 0; r < 32; ++r) t += s_bias[r * BN + tid];
+      part[Ktot * g.Cd + n0 + tid] = t;
+    }
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    // TMEM lane = (tap within its group) * 32 + channel; warps w and w + 4 split the BN columns of every group
+    const int j_tap = warp & 3;
+    constexpr int CHALF = BN / 2;
+    const int cbeg = (warp >> 2) * CHALF;
+    for (int gi = 0; gi < groups; ++gi) {
+      const int c = gi / TG, tg = gi - c * TG;
+      const int tap = tg * 4 + j_tap;
+      const uint32_t taddr = tmem_base + ((uint32_t)(j_tap * 32) << 16) + (uint32_t)(gi * BN);
+      const int64_t krow = (int64_t)tap * g.Cs + (cb0 + c) * 32 + lane;
+#pragma unroll 1
+      for (int c0 = cbeg; c0 < cbeg + CHALF; c0 += 16) {
+        float acc[16];
+        tmem_ld16(taddr + (uint32_t)c0, acc);      // warp-collective: issued for every tap slot, stored for real taps
+        if (tap < T) {
+          float* out = part + krow * g.Cd + n0 + c0;
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            *reinterpret_cast<float4*>(out + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ================================= MMA issuer =================================
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
+    if ((tid & 31) == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      // A: the four M blocks are four taps -> LBO = d rows; B: 32-channel N blocks 4 KB apart
+      const uint32_t a_desc0 = ((smem_u32(sA) & 0x3FFFF) >> 4) | ((uint32_t)(d * 8) << 16);
+      const uint32_t b_desc0 = desc_lo_mn(smem_u32(sB));
+      const uint32_t a_plane = (uint32_t)A_PLANE >> 4;
+      for (int ks = 0; ks < n_k; ++ks) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t ad_s = a_desc0 + (uint32_t)s * ((uint32_t)A_BYTES >> 4);
+        const uint32_t bd_s = b_desc0 + (uint32_t)s * (B_BYTES >> 4);
+        for (int gi = 0; gi < groups; ++gi) {
+          const int c = gi / TG, tg = gi - c * TG;
+          // group start: channel block c, tap tg*4 -> rows shifted by tg*4*d (8 descriptor units per row)
+          const uint32_t ad_g = ad_s + (uint32_t)c * (WR_A_CB >> 4) + (uint32_t)(tg * 4 * d) * 8u;
+          const uint32_t td = tmem_base + (uint32_t)(gi * BN);
+#pragma unroll
+          for (int kg = 0; kg < WR_POS / 8; ++kg) {
+            const uint32_t a_hi = ad_g + kg * 64u, b_hi = bd_s + kg * 64u;     // 8 positions = 1 KB = 64 units
+            const uint32_t acc = (ks > 0 || kg > 0) ? 1u : 0u;
+            if (SPLIT) {
+              const uint32_t a_lo = a_hi + a_plane, b_lo = b_hi + (B_PLANE >> 4);
+              umma_tf32_lo<DESC_HI_MN>(td, a_lo, b_hi, IDESC, acc);
+              umma_tf32_lo<DESC_HI_MN>(td, a_hi, b_lo, IDESC, 1u);
+              umma_tf32_lo<DESC_HI_MN>(td, a_hi, b_hi, IDESC, 1u);
+            } else {
+              umma_tf32_lo<DESC_HI_MN>(td, a_hi, b_hi, IDESC, acc);
+            }
+          }
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == NS) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
 // GEMM-layout weight [T][Cs][Cd] (cd contiguous)  ->  swizzled tile images [t'][Cs'/32][n_tile][BN x 128 B]
 //   role 0 (forward)      : n = cd, k = cs, t' = t
 //   role 1 (data gradient): n = cs, k = cd, t' = T-1-t   (stride-1 dgrad == forward conv with reversed taps)
@@ -1293,9 +1571,47 @@ int umma_wgrad_splits(const msmc_conv_geom& g, int bn) {
 }
 }  // namespace
 
+namespace {
+bool reuse_eligible(const msmc_conv_geom& g, int* tap_stride, int* n_taps, int* pad_rows);
+
+struct WgradReusePlan {
+  int tap_stride, n_taps, pad_rows, kc_cta, bn, splits, stages_per_split, total_stages, stages_per_batch, n_stages;
+};
+bool wgrad_reuse_plan(const msmc_conv_geom& g, bool split, WgradReusePlan* p) {
+  static const int enabled = [] { const char* e = getenv("MSMC_WGRAD_REUSE"); return e ? atoi(e) : 1; }();
+  if (!enabled) return false;
+  if (!reuse_eligible(g, &p->tap_stride, &p->n_taps, &p->pad_rows)) return false;
+  if (g.Cs % 32 != 0 || g.Cd % 32 != 0 || p->n_taps < 3) return false;
+  const int TG = (p->n_taps + 3) / 4;
+  if (WR_POS + (4 * TG - 1) * p->tap_stride > WR_ROWS) return false;
+  p->bn = (g.Cd % 64 == 0) ? 64 : 32;
+  p->kc_cta = ((g.Cs / 32) % 2 == 0) ? 2 : 1;
+  if (p->kc_cta * TG * p->bn > 512) p->kc_cta = 1;
+  if (p->kc_cta * TG * p->bn > 512) return false;
+  const int Ld = g.Hd * g.Wd;
+  p->stages_per_batch = ceil_div(Ld, WR_POS);
+  p->total_stages = g.B * p->stages_per_batch;
+  const int64_t tiles = (int64_t)(g.Cs / 32 / p->kc_cta) * (g.Cd / p->bn);
+  int64_t sp = std::max<int64_t>(1, (int64_t)num_sms() / tiles);
+  sp = std::min<int64_t>(sp, std::max<int64_t>(1, p->total_stages / 4));
+  const int64_t per = ((int64_t)g.KH * g.KW * g.Cs * g.Cd + g.Cd) * (int64_t)sizeof(float);
+  sp = std::max<int64_t>(1, std::min<int64_t>(sp, ((int64_t)128 << 20) / per));
+  p->stages_per_split = (int)ceil_div64(p->total_stages, sp);
+  p->splits = ceil_div(p->total_stages, p->stages_per_split);
+  const int stage_bytes = (split ? 2 : 1) * (p->kc_cta * WR_A_CB + (p->bn / 32) * 4096);
+  p->n_stages = std::min(WR_MAX_STAGES, (200 * 1024 - 32 * p->bn * 4) / stage_bytes);
+  return p->n_stages >= 2;
+}
+}  // namespace
+
 extern "C" int64_t msmc_conv_wgrad_umma_workspace(const msmc_conv_geom* gp) {
   if (!gp || gp->Cs % 32 != 0) return -1;
   const msmc_conv_geom& g = *gp;
+  {
+    WgradReusePlan rp;
+    if (wgrad_reuse_plan(g, true, &rp))
+      return (int64_t)rp.splits * ((int64_t)g.KH * g.KW * g.Cs * g.Cd + g.Cd) * (int64_t)sizeof(float);
+  }
   const int bn = umma_wgrad_bn(g.Cd);
   return (int64_t)umma_wgrad_splits(g, bn) * ((int64_t)g.KH * g.KW * g.Cs * g.Cd + g.Cd) * (int64_t)sizeof(float);
 }
@@ -1309,9 +1625,51 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
   MSMC_REQUIRE(!xf_needs_aux(g.src_xf) ||
                (src_aux && g.ld_saux % 4 == 0 && (reinterpret_cast<uintptr_t>(src_aux) & 15) == 0));
   MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || gout_aux);
+  const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
+  {
+    WgradReusePlan rp;
+    const bool vec_ok = (g.ld_dst % 4 == 0) && (reinterpret_cast<uintptr_t>(gout) & 15) == 0 &&
+                        (!xf_needs_aux(g.dst_xf) ||
+                         ((g.ld_daux % 4 == 0) && (reinterpret_cast<uintptr_t>(gout_aux) & 15) == 0));
+    // the plan (and the workspace it implies) never depends on `split`: both precisions use the same slicing
+    if (vec_ok && wgrad_reuse_plan(g, true, &rp)) {
+      MSMC_REQUIRE(workspace_bytes >= (int64_t)rp.splits * (Ktot * g.Cd + g.Cd) * (int64_t)sizeof(float));
+      WgradReuseArgs ra;
+      ra.g = g; ra.src = src; ra.src_aux = src_aux; ra.gout = gout; ra.gout_aux = gout_aux; ra.partial = workspace;
+      ra.Ls = g.Hs * g.Ws; ra.Ld = g.Hd * g.Wd;
+      ra.pad_rows = rp.pad_rows; ra.tap_stride = rp.tap_stride; ra.n_taps = rp.n_taps; ra.kc_cta = rp.kc_cta;
+      ra.stages_per_batch = rp.stages_per_batch; ra.total_stages = rp.total_stages;
+      ra.stages_per_split = rp.stages_per_split; ra.n_stages = rp.n_stages;
+      ra.want_bias = dbias != nullptr;
+      dim3 rgrid((unsigned)(g.Cs / 32 / rp.kc_cta), (unsigned)(g.Cd / rp.bn), (unsigned)rp.splits);
+      const size_t rsmem = 1024 + (size_t)rp.n_stages * (split ? 2 : 1) * (rp.kc_cta * WR_A_CB + (rp.bn / 32) * 4096) +
+                           32 * rp.bn * 4 + (2 * WR_MAX_STAGES + 1) * 8 + 16;
+      cudaStream_t rst = (cudaStream_t)stream;
+      const int rxfc = g.src_xf == MSMC_XF_NONE ? XFC_NONE
+                       : (g.src_xf == MSMC_XF_LRELU && g.src_slope > 0.f && g.src_slope < 1.f) ? XFC_LRELU
+                                                                                                : XFC_GENERIC;
+#define LAUNCH_WR_X(BN_, SPLIT_, X_)                                                                     \
+  do {                                                                                                   \
+    cudaFuncSetAttribute(conv_wgrad_reuse_kernel<BN_, SPLIT_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                         (int)rsmem);                                                                    \
+    conv_wgrad_reuse_kernel<BN_, SPLIT_, X_><<<rgrid, UMF_THREADS, rsmem, rst>>>(ra);                    \
+  } while (0)
+#define LAUNCH_WR(BN_, SPLIT_)                                         \
+  do {                                                                 \
+    if (rxfc == XFC_NONE) LAUNCH_WR_X(BN_, SPLIT_, XFC_NONE);          \
+    else if (rxfc == XFC_LRELU) LAUNCH_WR_X(BN_, SPLIT_, XFC_LRELU);   \
+    else LAUNCH_WR_X(BN_, SPLIT_, XFC_GENERIC);                        \
+  } while (0)
+      if (split) { if (rp.bn == 64) LAUNCH_WR(64, true); else LAUNCH_WR(32, true); }
+      else { if (rp.bn == 64) LAUNCH_WR(64, false); else LAUNCH_WR(32, false); }
+#undef LAUNCH_WR
+#undef LAUNCH_WR_X
+      MSMC_CHECK_LAUNCH();
+      return launch_wgrad_reduce(g, workspace, rp.splits, dw, dbias, stream);
+    }
+  }
   const int bn = umma_wgrad_bn(g.Cd);
   const int splits = umma_wgrad_splits(g, bn);
-  const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
   MSMC_REQUIRE(workspace_bytes >= (int64_t)splits * (Ktot * g.Cd + g.Cd) * (int64_t)sizeof(float));
   const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
   UmmaWgradArgs a;

@@ -6,6 +6,7 @@ Host-side differences only: no `.item()` host syncs inside the step (the referen
 implicit) -- losses are returned as 0-dim device tensors and read when they are logged; the window
 gather is tensor arithmetic instead of per-sample Python slicing, so the step is CUDA-graph capturable.
 """
+import contextlib
 import random
 
 import torch
@@ -57,6 +58,20 @@ class QuantizerLoss(nn.Module):
             loss["vq_loss"] = loss["vq_loss"] + self.lambda_pr * dd.pop("total_loss")
             loss.update(dd)
         return loss
+
+
+@contextlib.contextmanager
+def _frozen(module):
+    """parameters of `module` do not require grad inside the block (custom autograd Functions decide at forward time
+    which gradients they will produce, so restricting backward(inputs=...) alone would not skip the weight gradients)"""
+    params = [p for p in module.parameters() if p.requires_grad]
+    for p in params:
+        p.requires_grad_(False)
+    try:
+        yield
+    finally:
+        for p in params:
+            p.requires_grad_(True)
 
 
 class VQGANTrainer(BaseTrainer):
@@ -206,12 +221,14 @@ class VQGANTrainer(BaseTrainer):
             self.backward(d_loss, "discriminator")
             self.optimizer.step(["discriminator"])
             # ---- generator step (reference :182-201): D has already been updated, both passes are recomputed
-            fake_scores, fake_feats = disc(predict)
             if self.reference_schedule:
+                fake_scores, fake_feats = disc(predict)
                 _, real_feats = disc(target)
             else:
-                with torch.no_grad():
-                    _, real_feats = disc(target)
+                with _frozen(disc):         # D is a fixed function here: data gradients only, no weight gradients
+                    fake_scores, fake_feats = disc(predict)
+                    with torch.no_grad():
+                        _, real_feats = disc(target)
             adv = sum(F.mse_loss(s, torch.ones_like(s)) for s in fake_scores)
             fm = sum(F.l1_loss(a, b) for fa, fb in zip(fake_feats, real_feats) for a, b in zip(fa, fb))
             scale = self.lambda_fm if self.lambda_fm != "auto" else (g_loss / fm).detach()
