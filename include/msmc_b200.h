@@ -192,6 +192,14 @@ int msmc_mel_double_bwd(const float* gout, const float* mel, float* gmel, int64_
 int msmc_log_clamp_fwd(const float* x, float* y, int64_t n, float clip, void* stream);
 int msmc_log_clamp_bwd(const float* gy, const float* x, float* gx, int64_t n, float clip, void* stream);
 
+/* fused multi-tensor Adam / AdamW step with torch.optim semantics (reference trainers/optimizers/__init__.py:9-30
+ * builds torch.optim.Adam / AdamW per child module).  table = device array [4][n_tensors] of pointers
+ * (param, grad, exp_avg, exp_avg_sq), sizes[n_tensors] element counts, one CTA per (chunk_tensor[c], chunk_index[c])
+ * chunk of msmc_adam_chunk_elems() elements.  lr and step are DEVICE scalars (step = already incremented count) */
+int msmc_adam_chunk_elems(void);
+int msmc_adam_multi(const uint64_t* table, int32_t n_tensors, const int64_t* sizes, const int32_t* chunk_tensor,
+                    const int32_t* chunk_index, int32_t n_chunks, const float* lr, const float* step, float beta1,
+                    float beta2, float eps, float weight_decay, int32_t decoupled, void* stream);
 /* forward STFT framing (torch.stft center / reflect padding, audio.py:399, stft_loss.py:88-99): gather the overlapping
  * frames of x (B, L) into a dense (B*frames, win_p) matrix (columns >= win are zero) so the windowed DFT is one GEMM */
 int msmc_frame_unfold(const float* x, float* frames_out, int32_t B, int32_t L, int32_t frames, int32_t win,

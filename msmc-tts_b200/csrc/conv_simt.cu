@@ -723,8 +723,17 @@ __global__ void wgrad_reduce_kernel(const msmc_conv_geom g, const float* __restr
   const int64_t total = dbias ? per : Ktot * g.Cd;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (int64_t)gridDim.x * blockDim.x) {
+    // fixed summation order (deterministic); eight independent loads in flight instead of one
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * per + e];
+    int z = 0;
+    for (; z + 8 <= splits; z += 8) {
+      float t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = partial[(int64_t)(z + i) * per + e];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += t[i];
+    }
+    for (; z < splits; ++z) s += partial[(int64_t)z * per + e];
     if (e < Ktot * g.Cd) {
       const int64_t k = e / g.Cd;
       const int n = (int)(e - k * g.Cd);

@@ -14,3 +14,77 @@ int num_sms() {
 }  // namespace msmc
 extern "C" int msmc_version(void) { return 100; }
 extern "C" int msmc_num_sms(void) { return msmc::num_sms(); }
+
+// ------------------------------------------------------------------------------------------------
+// Fused multi-tensor Adam / AdamW step.  torch's capturable foreach path spends one tiny kernel per parameter on
+// the device-resident step size (lr / bias_correction1: ~1.2k launches per train step here) plus a dozen
+// multi-tensor passes; this is one launch per optimizer: block = one 16k-element chunk of one tensor, pointers
+// come from a device table, lr and the (already incremented) step count are device scalars so the launch is
+// CUDA-graph replayable.
+// ------------------------------------------------------------------------------------------------
+namespace msmc {
+namespace {
+constexpr int ADAM_CHUNK = 16384;
+constexpr int ADAM_THREADS = 256;
+
+__global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(
+    const unsigned long long* __restrict__ table, int n_tensors, const long long* __restrict__ sizes,
+    const int* __restrict__ chunk_tensor, const int* __restrict__ chunk_index, const float* __restrict__ lr_p,
+    const float* __restrict__ step_p, float beta1, float beta2, float eps, float weight_decay, int decoupled) {
+  const int t = chunk_tensor[blockIdx.x];
+  const long long beg = (long long)chunk_index[blockIdx.x] * ADAM_CHUNK;
+  const long long n = sizes[t];
+  const long long end = beg + ADAM_CHUNK < n ? beg + ADAM_CHUNK : n;
+  float* __restrict__ p = reinterpret_cast<float*>(table[t]);
+  const float* __restrict__ g = reinterpret_cast<const float*>(table[n_tensors + t]);
+  float* __restrict__ m = reinterpret_cast<float*>(table[2 * n_tensors + t]);
+  float* __restrict__ v = reinterpret_cast<float*>(table[3 * n_tensors + t]);
+  const float lr = *lr_p, step = *step_p;
+  const float bc1 = 1.f - powf(beta1, step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
+  const float step_size = lr / bc1;
+  const float decay = 1.f - lr * weight_decay;
+  auto upd = [&](float& pw, float gw, float& mw, float& vw) {
+    if (decoupled) pw *= decay;                 // AdamW: param.mul_(1 - lr * wd)
+    else gw = fmaf(weight_decay, pw, gw);       // Adam : grad + wd * param
+    mw = mw + (gw - mw) * (1.f - beta1);        // exp_avg.lerp_(grad, 1 - beta1)
+    vw = fmaf(vw, beta2, (1.f - beta2) * gw * gw);
+    const float denom = sqrtf(vw) / bc2_sqrt + eps;
+    pw -= step_size * (mw / denom);
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  if (vec) {
+    const long long end4 = beg + ((end - beg) & ~3LL);
+    for (long long i = beg + 4LL * threadIdx.x; i < end4; i += 4LL * ADAM_THREADS) {
+      float4 pw = *reinterpret_cast<float4*>(p + i);
+      const float4 gw = *reinterpret_cast<const float4*>(g + i);
+      float4 mw = *reinterpret_cast<float4*>(m + i);
+      float4 vw = *reinterpret_cast<float4*>(v + i);
+      upd(pw.x, gw.x, mw.x, vw.x); upd(pw.y, gw.y, mw.y, vw.y);
+      upd(pw.z, gw.z, mw.z, vw.z); upd(pw.w, gw.w, mw.w, vw.w);
+      *reinterpret_cast<float4*>(p + i) = pw;
+      *reinterpret_cast<float4*>(m + i) = mw;
+      *reinterpret_cast<float4*>(v + i) = vw;
+    }
+    for (long long i = end4 + threadIdx.x; i < end; i += ADAM_THREADS) upd(p[i], g[i], m[i], v[i]);
+  } else {
+    for (long long i = beg + threadIdx.x; i < end; i += ADAM_THREADS) upd(p[i], g[i], m[i], v[i]);
+  }
+}
+}  // namespace
+}  // namespace msmc
+
+extern "C" int msmc_adam_chunk_elems(void) { return msmc::ADAM_CHUNK; }
+
+extern "C" int msmc_adam_multi(const uint64_t* table, int32_t n_tensors, const int64_t* sizes,
+                               const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t n_chunks,
+                               const float* lr, const float* step, float beta1, float beta2, float eps,
+                               float weight_decay, int32_t decoupled, void* stream) {
+  MSMC_REQUIRE(table && sizes && chunk_tensor && chunk_index && lr && step && n_tensors > 0 && n_chunks > 0);
+  msmc::adam_multi_kernel<<<n_chunks, msmc::ADAM_THREADS, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned long long*>(table), n_tensors, reinterpret_cast<const long long*>(sizes),
+      chunk_tensor, chunk_index, lr, step, beta1, beta2, eps, weight_decay, decoupled);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}

@@ -416,6 +416,38 @@ class _PrepWeightFn(torch.autograd.Function):
         return dv, dg, None, None, None, None, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------ stream forks
+# Independent sub-networks (the 3 + 5 sub-discriminators, the parallel MRF blocks of one generator stage) are
+# enqueued on forked CUDA streams and joined afterwards: most of their kernels fill only part of the 148 SMs, so
+# running branches side by side hides tails, prologues and launch gaps.  autograd replays each branch's backward
+# on the stream its forward ran on, and a CUDA-graph capture records the fork/join as parallel graph branches.
+BRANCH_STREAMS = os.environ.get("MSMC_BRANCH_STREAMS", "1") != "0"
+_side_streams = {}
+_in_branch = [False]
+
+
+def run_branches(fns):
+    """[f() for f in fns] with every f on its own side stream (sequential when disabled, nested or on CPU)"""
+    if not BRANCH_STREAMS or len(fns) < 2 or _in_branch[0] or not torch.cuda.is_available():
+        return [f() for f in fns]
+    main = torch.cuda.current_stream()
+    pool = _side_streams.setdefault(main.device, [])
+    while len(pool) < len(fns):
+        pool.append(torch.cuda.Stream(device=main.device))
+    outs = []
+    _in_branch[0] = True
+    try:
+        for f, s in zip(fns, pool):
+            s.wait_stream(main)
+            with torch.cuda.stream(s):
+                outs.append(f())
+    finally:
+        _in_branch[0] = False
+    for s in pool[:len(fns)]:
+        main.wait_stream(s)
+    return outs
+
+
 # id of the trainer step in flight (0 = none): layers share one re-parametrised weight per parameter version inside it
 PREP_SCOPE = [0]
 _prep_scope_ids = [0]

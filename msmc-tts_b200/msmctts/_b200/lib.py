@@ -67,6 +67,9 @@ SIGNATURES = {
     "msmc_mel_double_bwd": (C.c_int, [_P, _P, _P, _I64, _F, _F, _P]),
     "msmc_log_clamp_fwd": (C.c_int, [_P, _P, _I64, _F, _P]),
     "msmc_log_clamp_bwd": (C.c_int, [_P, _P, _P, _I64, _F, _P]),
+    "msmc_adam_chunk_elems": (C.c_int, []),
+    "msmc_adam_multi": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  _I32, _P]),
     "msmc_frame_unfold": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "msmc_overlap_add_fold": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "msmc_gated_act_fwd": (C.c_int, [_P, _P, _I64, _I32, _P]),

@@ -6,6 +6,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from msmctts._b200 import functional as Fn
 from msmctts._b200 import layers as Ly
 from msmctts.utils.audio import TorchSTFT
 from .common import get_padding
@@ -64,13 +65,17 @@ class MultiResolutionDiscriminator(nn.Module):
             DiscriminatorR(2 if domain == "double" else 1, c) for _, c in zip(hop_lengths, hidden_channels)])
 
     def forward(self, x):
-        scores, feats = [], []
+        outs = Fn.run_branches(self.branches(x))
+        return [o[0] for o in outs], [o[1] for o in outs]
+
+    def branches(self, x):
+        """one closure per resolution -> (score, feature maps) in the reference's (B, C, H, W) layout"""
         wav = x.reshape(x.shape[0], -1)
-        for stft, disc in zip(self.stfts, self.discriminators):
+
+        def one(stft, disc):
             score, feat = disc.forward_cl(stft.transform_cl(wav))
-            scores.append(score.permute(0, 3, 2, 1))
-            feats.append([f.permute(0, 3, 2, 1) for f in feat])
-        return scores, feats
+            return score.permute(0, 3, 2, 1), [f.permute(0, 3, 2, 1) for f in feat]
+        return [(lambda s=s, d=d: one(s, d)) for s, d in zip(self.stfts, self.discriminators)]
 
 
 class DiscriminatorP(nn.Module):
@@ -110,12 +115,11 @@ class MultiPeriodDiscriminator(nn.Module):
         self.discriminators = nn.ModuleList([DiscriminatorP(p, channels, max_channels) for p in periods])
 
     def forward(self, y):
-        outputs, fmaps = [], []
-        for d in self.discriminators:
-            o, f = d(y)
-            outputs.append(o)
-            fmaps.append(f)
-        return outputs, fmaps
+        outs = Fn.run_branches(self.branches(y))
+        return [o[0] for o in outs], [o[1] for o in outs]
+
+    def branches(self, y):
+        return [(lambda d=d: d(y)) for d in self.discriminators]
 
 
 class Discriminator(nn.Module):
@@ -127,6 +131,6 @@ class Discriminator(nn.Module):
     def forward(self, y):
         if y.dim() == 2:
             y = y.unsqueeze(1)
-        mrd_outputs, mrd_fmaps = self.mrd(y)
-        mpd_outputs, mpd_fmaps = self.mpd(y)
-        return mrd_outputs + mpd_outputs, mrd_fmaps + mpd_fmaps
+        # all 3 + 5 sub-discriminators are independent: one fork, eight branches, one join
+        outs = Fn.run_branches(self.mrd.branches(y) + self.mpd.branches(y))
+        return [o[0] for o in outs], [o[1] for o in outs]

@@ -3,6 +3,7 @@ forward(mel (B, C, L)) -> (B, 1, L*prod(upsample_rates)) keeps the reference sig
 (B, L, C) directly and is what MSMCVQGAN calls (no NCL<->NLC transposes on the hot path)."""
 from torch import nn
 
+from msmctts._b200 import functional as Fn
 from msmctts._b200 import layers as Ly
 from .common import LRELU_SLOPE, ResBlock1
 
@@ -29,10 +30,11 @@ class Generator(nn.Module):
         x = self.conv_pre(x)
         for i in range(self.num_upsamples):
             x = self.ups[i](x, pre_slope=LRELU_SLOPE)
-            xs = None
-            for j in range(self.num_kernels):
-                r = self.resblocks[i * self.num_kernels + j](x)
-                xs = r if xs is None else xs + r
+            blocks = self.resblocks[i * self.num_kernels:(i + 1) * self.num_kernels]
+            rs = Fn.run_branches([(lambda b=b, x=x: b(x)) for b in blocks])      # independent MRF branches
+            xs = rs[0]
+            for r in rs[1:]:
+                xs = xs + r
             x = xs / self.num_kernels
         # F.leaky_relu default slope 0.01 (generator.py:52), conv_post, tanh -- one launch
         return self.conv_post(x, pre_slope=0.01, post="tanh")

@@ -1,5 +1,6 @@
-"""Per-child-module optimizers (reference trainers/optimizers/__init__.py:9-78).  Out of the kernel hot path
-(host-side, torch.optim); built with capturable=True on CUDA so a whole train step can be graph-captured."""
+"""Per-child-module optimizers (reference trainers/optimizers/__init__.py:9-78).  On CUDA the step is the fused
+multi-tensor kernel (fused.py) so a whole train step can be graph-captured; CPU tensors (host-side
+tests) get torch.optim."""
 import re
 
 import torch
@@ -11,9 +12,10 @@ def get_optimizer(parameters, config):
     name = config._name
     kw = dict(lr=config.learning_rate, betas=tuple(config.betas), eps=config.eps, weight_decay=config.weight_decay)
     if parameters and parameters[0].is_cuda:
-        kw["capturable"] = True
-        # device-resident learning rate: the scheduler can change it between CUDA-graph replays
-        kw["lr"] = torch.tensor(float(config.learning_rate), dtype=torch.float32, device=parameters[0].device)
+        if name in ("Adam", "AdamW"):
+            # one fused multi-tensor launch per optimizer, device-resident lr and step (CUDA-graph replayable)
+            from .fused import FusedAdam
+            return FusedAdam(parameters, decoupled=(name == "AdamW"), **kw)
     if name == "Adam":
         return Adam(parameters, **kw)
     if name == "AdamW":

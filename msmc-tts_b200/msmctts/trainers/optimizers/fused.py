@@ -1,0 +1,125 @@
+"""Adam / AdamW whose whole step is ONE launch of msmc_adam_multi.
+
+State layout and hyper-parameter names follow torch.optim.Adam(W) (`step`, `exp_avg`, `exp_avg_sq` per parameter,
+param_groups with lr/betas/eps/weight_decay), so reference optimizer checkpoints (reference
+trainers/optimizers/__init__.py:47-57 stores torch's state_dict) load unchanged.  `lr` is a device scalar: the
+scheduler can change it between CUDA-graph replays.  Update rule == torch's single-tensor path
+(torch/optim/adam.py): decoupled decay for AdamW, L2 term added to the gradient for Adam."""
+import ctypes as C
+
+import torch
+
+from msmctts._b200 import lib as L
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False):
+        params = list(params)
+        if not params:
+            raise ValueError("optimizer got an empty parameter list")
+        dev = params[0].device
+        if not torch.is_tensor(lr):
+            lr = torch.tensor(float(lr), dtype=torch.float32, device=dev)
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, decoupled=decoupled,
+                        amsgrad=False, maximize=False, capturable=True, foreach=None, fused=None,
+                        differentiable=False)
+        super().__init__(params, defaults)
+        self._plans = {}
+
+    # ---------------------------------------------------------------------------------------------- state
+    def _ensure_state(self, group):
+        """torch-compatible per-parameter state; every `step` entry of a group aliases ONE device counter"""
+        counter = group.get("_step")
+        if counter is None:
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st and "step" in st:
+                    counter = st["step"].detach().to(device=p.device, dtype=torch.float32).reshape(()).clone()
+                    break
+            if counter is None:
+                counter = torch.zeros((), dtype=torch.float32, device=group["params"][0].device)
+            group["_step"] = counter
+        for p in group["params"]:
+            st = self.state[p]
+            if "exp_avg" not in st:
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["step"] = counter
+        return counter
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        for group in self.param_groups:          # re-tie the per-parameter counters to one device scalar
+            group.pop("_step", None)
+            group.setdefault("decoupled", self.defaults["decoupled"])   # torch's groups do not carry it
+            if not torch.is_tensor(group["lr"]):
+                group["lr"] = torch.tensor(float(group["lr"]), dtype=torch.float32,
+                                           device=group["params"][0].device)
+        self._plans = {}
+
+    def state_dict(self):
+        sd = super().state_dict()
+        for g in sd["param_groups"]:
+            g.pop("_step", None)
+        return sd
+
+    # ----------------------------------------------------------------------------------------------- step
+    def _plan(self, gi, active):
+        """static per (group, set of parameters with gradients): sizes and chunk map on the device"""
+        key = (gi, tuple(active))
+        plan = self._plans.get(key)
+        if plan is None:
+            group = self.param_groups[gi]
+            ps = [group["params"][i] for i in active]
+            dev = ps[0].device
+            chunk = L.load().msmc_adam_chunk_elems()
+            sizes = [p.numel() for p in ps]
+            ct, ci = [], []
+            for t, n in enumerate(sizes):
+                for c in range((n + chunk - 1) // chunk):
+                    ct.append(t)
+                    ci.append(c)
+            plan = {
+                "sizes": torch.tensor(sizes, dtype=torch.int64, device=dev),
+                "ct": torch.tensor(ct, dtype=torch.int32, device=dev),
+                "ci": torch.tensor(ci, dtype=torch.int32, device=dev),
+                "host": torch.empty(4 * len(ps), dtype=torch.int64).pin_memory(),
+                "table": torch.empty(4 * len(ps), dtype=torch.int64, device=dev),
+                "n_chunks": len(ct),
+            }
+            self._plans[key] = plan
+        return plan
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            active = [i for i, p in enumerate(group["params"]) if p.grad is not None]
+            if not active:
+                continue
+            counter = self._ensure_state(group)
+            plan = self._plan(gi, active)
+            n = len(active)
+            host = plan["host"]
+            for k, i in enumerate(active):
+                p = group["params"][i]
+                g = p.grad
+                if not (p.is_contiguous() and g.is_contiguous() and p.dtype == torch.float32 and
+                        g.dtype == torch.float32):
+                    raise L.MsmcError("FusedAdam needs contiguous fp32 parameters and gradients")
+                st = self.state[p]
+                host[k] = p.data_ptr()
+                host[n + k] = g.data_ptr()
+                host[2 * n + k] = st["exp_avg"].data_ptr()
+                host[3 * n + k] = st["exp_avg_sq"].data_ptr()
+            plan["table"].copy_(host, non_blocking=True)      # graph-capturable H2D from pinned memory
+            counter.add_(1.0)
+            b1, b2 = group["betas"]
+            L.call("msmc_adam_multi", L.ptr(plan["table"]), n, L.ptr(plan["sizes"]), L.ptr(plan["ct"]),
+                   L.ptr(plan["ci"]), plan["n_chunks"], L.ptr(group["lr"]), L.ptr(counter), C.c_float(b1),
+                   C.c_float(b2), C.c_float(group["eps"]), C.c_float(group["weight_decay"]),
+                   1 if group["decoupled"] else 0)
+        return loss
