@@ -200,6 +200,16 @@ int msmc_adam_chunk_elems(void);
 int msmc_adam_multi(const uint64_t* table, int32_t n_tensors, const int64_t* sizes, const int32_t* chunk_tensor,
                     const int32_t* chunk_index, int32_t n_chunks, const float* lr, const float* step, float beta1,
                     float beta2, float eps, float weight_decay, int32_t decoupled, void* stream);
+/* feature-matching loss over a list of tensor pairs (reference trainers/msmctts_trainer.py:186-190: the sum of 55
+ * F.l1_loss(fake_fmap, real_fmap) terms): out[0] = sum_t mean|a_t - b_t|.  table = device array [2][n_tensors] of
+ * pointers (a, b) ([3][n_tensors] with the gradient buffers ga for _bwd), chunks of msmc_l1_chunk_elems() elements,
+ * partial = n_chunks floats of workspace; the reduction order is fixed (deterministic).
+ * _bwd: ga_t = gout[0] * sign(a_t - b_t) / n_t   (gout is a DEVICE scalar) */
+int msmc_l1_chunk_elems(void);
+int msmc_l1_multi_fwd(const uint64_t* table, int32_t n_tensors, const int64_t* sizes, const int32_t* chunk_tensor,
+                      const int32_t* chunk_index, int32_t n_chunks, float* partial, float* out, void* stream);
+int msmc_l1_multi_bwd(const uint64_t* table, int32_t n_tensors, const int64_t* sizes, const int32_t* chunk_tensor,
+                      const int32_t* chunk_index, int32_t n_chunks, const float* gout, void* stream);
 /* forward STFT framing (torch.stft center / reflect padding, audio.py:399, stft_loss.py:88-99): gather the overlapping
  * frames of x (B, L) into a dense (B*frames, win_p) matrix (columns >= win are zero) so the windowed DFT is one GEMM */
 int msmc_frame_unfold(const float* x, float* frames_out, int32_t B, int32_t L, int32_t frames, int32_t win,

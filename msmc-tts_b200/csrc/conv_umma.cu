@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
       tmem_ld16(taddr + (uint32_t)c0, acc);
       if (row_ok) {
         const bool full16 = n0 + c0 + 16 <= g.Cd;
-        if (full16 && !dneed_aux && (g.ld_dst & 3) == 0 && (!a.residual || (g.ld_res & 3) == 0)) {
+        if (full16 && (!dneed_aux || ((g.ld_daux & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dst_aux) & 15) == 0)) && (g.ld_dst & 3) == 0 && (!a.residual || (g.ld_res & 3) == 0)) {
           // fast path: 16 full columns, vector loads of bias / residual, vector stores
           float* out = a.dst + m * g.ld_dst + n0 + c0;
 #pragma unroll
@@ -442,8 +442,10 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
               x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
             }
             if (g.dst_xf != MSMC_XF_NONE) {
-              x.x = apply_xf(g.dst_xf, g.dst_slope, x.x, 0.f); x.y = apply_xf(g.dst_xf, g.dst_slope, x.y, 0.f);
-              x.z = apply_xf(g.dst_xf, g.dst_slope, x.z, 0.f); x.w = apply_xf(g.dst_xf, g.dst_slope, x.w, 0.f);
+              float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (dneed_aux) av = __ldg(reinterpret_cast<const float4*>(a.dst_aux + m * g.ld_daux + n0 + c0 + j));
+              x.x = apply_xf(g.dst_xf, g.dst_slope, x.x, av.x); x.y = apply_xf(g.dst_xf, g.dst_slope, x.y, av.y);
+              x.z = apply_xf(g.dst_xf, g.dst_slope, x.z, av.z); x.w = apply_xf(g.dst_xf, g.dst_slope, x.w, av.w);
             }
             if (a.residual) {
               const float4 rv = __ldg(reinterpret_cast<const float4*>(a.residual + m * g.ld_res + n0 + c0 + j));
@@ -673,7 +675,7 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
       tmem_ld16(taddr + (uint32_t)c0, acc);
       if (row_ok) {
         const bool full16 = n0 + c0 + 16 <= g.Cd;
-        if (full16 && !dneed_aux && (g.ld_dst & 3) == 0 && (!a.residual || (g.ld_res & 3) == 0)) {
+        if (full16 && (!dneed_aux || ((g.ld_daux & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dst_aux) & 15) == 0)) && (g.ld_dst & 3) == 0 && (!a.residual || (g.ld_res & 3) == 0)) {
           // fast path: 16 full columns, vector loads of bias / residual, vector stores
           float* out = a.dst + m * g.ld_dst + n0 + c0;
 #pragma unroll
@@ -684,8 +686,10 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
               x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
             }
             if (g.dst_xf != MSMC_XF_NONE) {
-              x.x = apply_xf(g.dst_xf, g.dst_slope, x.x, 0.f); x.y = apply_xf(g.dst_xf, g.dst_slope, x.y, 0.f);
-              x.z = apply_xf(g.dst_xf, g.dst_slope, x.z, 0.f); x.w = apply_xf(g.dst_xf, g.dst_slope, x.w, 0.f);
+              float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (dneed_aux) av = __ldg(reinterpret_cast<const float4*>(a.dst_aux + m * g.ld_daux + n0 + c0 + j));
+              x.x = apply_xf(g.dst_xf, g.dst_slope, x.x, av.x); x.y = apply_xf(g.dst_xf, g.dst_slope, x.y, av.y);
+              x.z = apply_xf(g.dst_xf, g.dst_slope, x.z, av.z); x.w = apply_xf(g.dst_xf, g.dst_slope, x.w, av.w);
             }
             if (a.residual) {
               const float4 rv = __ldg(reinterpret_cast<const float4*>(a.residual + m * g.ld_res + n0 + c0 + j));
@@ -1447,6 +1451,11 @@ __global__ void weight_image_kernel(const float* __restrict__ w, float* __restri
 // N tile: the widest of {128, 64, 32} that still yields at least ~one CTA per SM (small-M layers such as the
 // FFN / MPD convs would otherwise launch a few dozen CTAs on a 148-SM part)
 int umma_pick_bn(int cd, int64_t rows) {
+  // bring-up / sweep override (profiles/sweep_bn.py): MSMC_FORCE_BN=32|64|128, read per call
+  if (const char* e = getenv("MSMC_FORCE_BN")) {
+    const int f = atoi(e);
+    if ((f == 32 || f == 64 || f == 128) && !(f > 32 && cd <= f / 2)) return f;
+  }
   const int64_t mt = ceil_div64(rows, UM_BM);
   const int64_t want = num_sms();
   const int cands[3] = {128, 64, 32};

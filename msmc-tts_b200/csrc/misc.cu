@@ -88,3 +88,117 @@ extern "C" int msmc_adam_multi(const uint64_t* table, int32_t n_tensors, const i
   MSMC_CHECK_LAUNCH();
   return MSMC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Feature-matching loss over a LIST of tensor pairs in one launch (+ one tiny reduce):
+//   loss = sum_t mean |a_t - b_t|          (reference trainers/msmctts_trainer.py:186-190: 55 F.l1_loss terms)
+// torch spends ~7 kernels per pair (sub, abs, mean; sign, mul, mul, add in backward) = ~400 launches per step;
+// this is 2 + 1.  Block = one 16k-element chunk of one pair; per-block partials are reduced in a fixed order by a
+// single block, so the result is run-to-run deterministic.  Backward: ga_t = g * sign(a_t - b_t) / n_t.
+// ------------------------------------------------------------------------------------------------
+namespace msmc {
+namespace {
+constexpr int L1_CHUNK = 16384;
+constexpr int L1_THREADS = 256;
+
+__device__ __forceinline__ float block_sum_256(float v, float* sh) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (L1_THREADS / 32) ? sh[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+  }
+  return t;   // valid in warp 0
+}
+
+__global__ void __launch_bounds__(L1_THREADS) l1_multi_fwd_kernel(
+    const unsigned long long* __restrict__ table, int n_tensors, const long long* __restrict__ sizes,
+    const int* __restrict__ chunk_tensor, const int* __restrict__ chunk_index, float* __restrict__ partial) {
+  __shared__ float sh[L1_THREADS / 32];
+  const int t = chunk_tensor[blockIdx.x];
+  const long long beg = (long long)chunk_index[blockIdx.x] * L1_CHUNK;
+  const long long n = sizes[t];
+  const long long end = beg + L1_CHUNK < n ? beg + L1_CHUNK : n;
+  const float* __restrict__ a = reinterpret_cast<const float*>(table[t]);
+  const float* __restrict__ b = reinterpret_cast<const float*>(table[n_tensors + t]);
+  float acc = 0.f;
+  const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  if (vec) {
+    const long long end4 = beg + ((end - beg) & ~3LL);
+    for (long long i = beg + 4LL * threadIdx.x; i < end4; i += 4LL * L1_THREADS) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(a + i));
+      const float4 y = __ldg(reinterpret_cast<const float4*>(b + i));
+      acc += (fabsf(x.x - y.x) + fabsf(x.y - y.y)) + (fabsf(x.z - y.z) + fabsf(x.w - y.w));
+    }
+    for (long long i = end4 + threadIdx.x; i < end; i += L1_THREADS) acc += fabsf(a[i] - b[i]);
+  } else {
+    for (long long i = beg + threadIdx.x; i < end; i += L1_THREADS) acc += fabsf(a[i] - b[i]);
+  }
+  const float tot = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot / (float)n;
+}
+
+__global__ void __launch_bounds__(L1_THREADS) l1_multi_reduce_kernel(const float* __restrict__ partial, int n_chunks,
+                                                                     float* __restrict__ out) {
+  __shared__ float sh[L1_THREADS / 32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n_chunks; i += L1_THREADS) acc += partial[i];
+  const float tot = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) out[0] = tot;
+}
+
+__global__ void __launch_bounds__(L1_THREADS) l1_multi_bwd_kernel(
+    const unsigned long long* __restrict__ table, int n_tensors, const long long* __restrict__ sizes,
+    const int* __restrict__ chunk_tensor, const int* __restrict__ chunk_index, const float* __restrict__ gout) {
+  const int t = chunk_tensor[blockIdx.x];
+  const long long beg = (long long)chunk_index[blockIdx.x] * L1_CHUNK;
+  const long long n = sizes[t];
+  const long long end = beg + L1_CHUNK < n ? beg + L1_CHUNK : n;
+  const float* __restrict__ a = reinterpret_cast<const float*>(table[t]);
+  const float* __restrict__ b = reinterpret_cast<const float*>(table[n_tensors + t]);
+  float* __restrict__ ga = reinterpret_cast<float*>(table[2 * n_tensors + t]);
+  const float s = gout[0] / (float)n;
+  auto sg = [s](float x, float y) { const float d = x - y; return d > 0.f ? s : (d < 0.f ? -s : 0.f); };
+  const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(ga)) & 15) == 0;
+  if (vec) {
+    const long long end4 = beg + ((end - beg) & ~3LL);
+    for (long long i = beg + 4LL * threadIdx.x; i < end4; i += 4LL * L1_THREADS) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(a + i));
+      const float4 y = __ldg(reinterpret_cast<const float4*>(b + i));
+      *reinterpret_cast<float4*>(ga + i) = make_float4(sg(x.x, y.x), sg(x.y, y.y), sg(x.z, y.z), sg(x.w, y.w));
+    }
+    for (long long i = end4 + threadIdx.x; i < end; i += L1_THREADS) ga[i] = sg(a[i], b[i]);
+  } else {
+    for (long long i = beg + threadIdx.x; i < end; i += L1_THREADS) ga[i] = sg(a[i], b[i]);
+  }
+}
+}  // namespace
+}  // namespace msmc
+
+extern "C" int msmc_l1_chunk_elems(void) { return msmc::L1_CHUNK; }
+
+extern "C" int msmc_l1_multi_fwd(const uint64_t* table, int32_t n_tensors, const int64_t* sizes,
+                                 const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t n_chunks,
+                                 float* partial, float* out, void* stream) {
+  MSMC_REQUIRE(table && sizes && chunk_tensor && chunk_index && partial && out && n_tensors > 0 && n_chunks > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  msmc::l1_multi_fwd_kernel<<<n_chunks, msmc::L1_THREADS, 0, st>>>(
+      reinterpret_cast<const unsigned long long*>(table), n_tensors, reinterpret_cast<const long long*>(sizes),
+      chunk_tensor, chunk_index, partial);
+  msmc::l1_multi_reduce_kernel<<<1, msmc::L1_THREADS, 0, st>>>(partial, n_chunks, out);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+
+extern "C" int msmc_l1_multi_bwd(const uint64_t* table, int32_t n_tensors, const int64_t* sizes,
+                                 const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t n_chunks,
+                                 const float* gout, void* stream) {
+  MSMC_REQUIRE(table && sizes && chunk_tensor && chunk_index && gout && n_tensors > 0 && n_chunks > 0);
+  msmc::l1_multi_bwd_kernel<<<n_chunks, msmc::L1_THREADS, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned long long*>(table), n_tensors, reinterpret_cast<const long long*>(sizes),
+      chunk_tensor, chunk_index, gout);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}

@@ -209,6 +209,31 @@ class _ConvFn(torch.autograd.Function):
         pre = (L.XF_LRELU, cfg.pre_slope, None) if cfg.pre_slope is not None else (L.XF_NONE, 0.0, None)
         s_kh, s_kw, s_cs, s_cd = cfg.wstr
         gx = gw = gb = None
+        # The weight gradient is off the critical path (only the optimizer reads it) while the data gradient feeds
+        # the next layer's backward: enqueue wgrad on a side stream first, the data gradient on the current stream,
+        # and join before returning.  Outputs are allocated on the current stream (allocator ownership).
+        side = None
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty_like(w) if w.is_contiguous() else torch.zeros_like(w)
+            want_b = ctx.has_bias and ctx.needs_input_grad[2]
+            if want_b and not cfg.transposed:
+                gb = torch.empty(cfg.Cd, dtype=torch.float32, device=x.device)
+            cur = None
+            if WGRAD_STREAM and ctx.needs_input_grad[0] and x.is_cuda:
+                cur, side = _wgrad_side_stream()
+                side.wait_stream(cur)
+            with torch.cuda.stream(side) if side is not None else _NullCtx():
+                if not cfg.transposed:
+                    _launch_wgrad(x, gy, gw, cfg.wstr, gb, cfg.KH, cfg.KW, cfg.sh, cfg.sw, cfg.dh, cfg.dw, cfg.ph,
+                                  cfg.pw, cfg.reflect, src_xf=pre, gout_xf=gmod)
+                else:
+                    # roles swap: the op's output plays the gathered source, the op's input plays "gout"
+                    _launch_wgrad(gy, x, gw, (s_kh, s_kw, s_cd, s_cs), None, cfg.KH, cfg.KW, cfg.sh, cfg.sw, cfg.dh,
+                                  cfg.dw, cfg.ph, cfg.pw, False, src_xf=gmod, gout_xf=pre)
+            if want_b and cfg.transposed:
+                gb = _post_grad(gy, y, cfg.post).sum(dim=(0, 1, 2))
+        elif ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = _post_grad(gy, y, cfg.post).sum(dim=(0, 1, 2))
         if ctx.needs_input_grad[0]:
             dmod = (L.XF_MUL_DLRELU, cfg.pre_slope, x) if cfg.pre_slope is not None else (L.XF_NONE, 0.0, None)
             if cfg.reflect:
@@ -263,23 +288,32 @@ class _ConvFn(torch.autograd.Function):
                     _launch_conv(gy, w, (s_kh, s_kw, s_cd, s_cs), None, None, gx, cfg.KH, cfg.KW, cfg.sh, cfg.sw,
                                  cfg.dh, cfg.dw, cfg.ph, cfg.pw, False, not cfg.transposed, src_xf=gmod,
                                  dst_xf=dmod)
-        if ctx.needs_input_grad[1]:
-            gw = torch.empty_like(w) if w.is_contiguous() else torch.zeros_like(w)
-            want_b = ctx.has_bias and ctx.needs_input_grad[2]
-            if not cfg.transposed:
-                gb = torch.empty(cfg.Cd, dtype=torch.float32, device=x.device) if want_b else None
-                _launch_wgrad(x, gy, gw, cfg.wstr, gb, cfg.KH, cfg.KW, cfg.sh, cfg.sw, cfg.dh, cfg.dw, cfg.ph,
-                              cfg.pw, cfg.reflect, src_xf=pre, gout_xf=gmod)
-            else:
-                # roles swap: the op's output plays the gathered source, the op's input plays "gout"
-                _launch_wgrad(gy, x, gw, (s_kh, s_kw, s_cd, s_cs), None, cfg.KH, cfg.KW, cfg.sh, cfg.sw, cfg.dh,
-                              cfg.dw, cfg.ph, cfg.pw, False, src_xf=gmod, gout_xf=pre)
-                if want_b:
-                    gb = _post_grad(gy, y, cfg.post).sum(dim=(0, 1, 2))
-        elif ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = _post_grad(gy, y, cfg.post).sum(dim=(0, 1, 2))
+        if side is not None:
+            cur.wait_stream(side)
         gres = gy if (ctx.has_res and ctx.needs_input_grad[3]) else None
         return gx, gw, gb, gres, None
+
+
+WGRAD_STREAM = os.environ.get("MSMC_WGRAD_STREAM", "1") != "0"
+_wgrad_streams = {}
+
+
+class _NullCtx(object):
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _wgrad_side_stream():
+    """(current stream, its dedicated weight-gradient side stream)"""
+    cur = torch.cuda.current_stream()
+    key = (cur.device.index, cur.cuda_stream)
+    s = _wgrad_streams.get(key)
+    if s is None:
+        s = _wgrad_streams[key] = torch.cuda.Stream(device=cur.device)
+    return cur, s
 
 
 def _post_grad(gy, y, post):
@@ -567,6 +601,132 @@ class _TripleFn(torch.autograd.Function):
 
 def vq_triple_loss(pred, embed, target, n_heads, dim, margin=1e-6, reduction="mean"):
     return _TripleFn.apply(pred, embed, target, n_heads, dim, margin, reduction == "mean")
+
+
+# ------------------------------------------------------------------------------ multi-tensor L1 (feature matching)
+_l1_plans = {}
+_l1_graph_plans = []
+
+
+def _dense_perm(t):
+    """permutation under which `t` is contiguous (feature maps are permuted views of channels-last buffers), or None"""
+    order = sorted(range(t.dim()), key=lambda d: (-t.stride(d), d))
+    return order if t.permute(order).is_contiguous() else None
+
+
+def _staging(rows_x_n, device):
+    return (torch.empty(rows_x_n, dtype=torch.int64).pin_memory(),
+            torch.empty(rows_x_n, dtype=torch.int64, device=device))
+
+
+def _l1_plan(sizes, device, with_grad):
+    """chunk map (device, immutable) + pointer-table staging.  A plan used inside a CUDA-graph capture gets PRIVATE
+    staging buffers (taken from spares allocated by an earlier eager call): the captured H2D copy re-reads the pinned
+    buffer on every replay, so later eager calls must not overwrite it."""
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (tuple(sizes), device.index, with_grad)
+    plan = _l1_plans.get(key)
+    rows = 3 if with_grad else 2
+    if plan is None:
+        if capturing:
+            raise L.MsmcError("l1_multi: run one eager step with these shapes before capturing a CUDA graph")
+        chunk = L.load().msmc_l1_chunk_elems()
+        ct, ci = [], []
+        for t, n in enumerate(sizes):
+            for c in range((n + chunk - 1) // chunk):
+                ct.append(t)
+                ci.append(c)
+        host, table = _staging(rows * len(sizes), device)
+        plan = {"sizes": torch.tensor(sizes, dtype=torch.int64, device=device),
+                "ct": torch.tensor(ct, dtype=torch.int32, device=device),
+                "ci": torch.tensor(ci, dtype=torch.int32, device=device),
+                "host": host, "table": table, "n_chunks": len(ct), "event": None,
+                "spares": [_staging(rows * len(sizes), device) for _ in range(2)]}
+        _l1_plans[key] = plan
+    if capturing:
+        if not plan["spares"]:
+            raise L.MsmcError("l1_multi: no private staging buffer left for another CUDA-graph capture")
+        host, table = plan["spares"].pop()
+        plan = dict(plan, host=host, table=table, spares=None)
+        _l1_graph_plans.append(plan)
+    return plan
+
+
+def _l1_fill_table(plan, rows):
+    """pointer table -> device through the plan's pinned staging buffer (graph-capturable H2D copy)"""
+    capturing = torch.cuda.is_current_stream_capturing()
+    if not capturing and plan["event"] is not None:
+        plan["event"].synchronize()          # the previous eager copy out of the staging buffer has run
+    host = plan["host"]
+    k = 0
+    for row in rows:
+        for t in row:
+            host[k] = t.data_ptr()
+            k += 1
+    plan["table"].copy_(host, non_blocking=True)
+    if not capturing:
+        plan["event"] = torch.cuda.Event()
+        plan["event"].record()
+
+
+class _L1MultiFn(torch.autograd.Function):
+    """sum_t mean|a_t - b_t| over a list of pairs in 2 launches (forward) + 1 (backward); gradients only w.r.t. a_t"""
+
+    @staticmethod
+    def forward(ctx, n, *tensors):
+        a_list, b_list = tensors[:n], tensors[n:]
+        da, db, perms = [], [], []
+        for a, b in zip(a_list, b_list):
+            assert a.shape == b.shape
+            L.require_cuda(a, b)
+            perm = _dense_perm(a)
+            if perm is None:
+                perm = list(range(a.dim()))
+                a = a.contiguous()
+            a_d = a.permute(perm)
+            b_d = b.permute(perm)
+            if not b_d.is_contiguous():
+                b_d = b_d.contiguous()
+            da.append(a_d)
+            db.append(b_d)
+            perms.append(perm)
+        dev = da[0].device
+        plan = _l1_plan([t.numel() for t in da], dev, False)
+        _l1_fill_table(plan, (da, db))
+        partial = torch.empty(plan["n_chunks"], dtype=torch.float32, device=dev)
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        L.call("msmc_l1_multi_fwd", L.ptr(plan["table"]), n, L.ptr(plan["sizes"]), L.ptr(plan["ct"]),
+               L.ptr(plan["ci"]), plan["n_chunks"], L.ptr(partial), L.ptr(out))
+        ctx.n, ctx.perms = n, perms
+        ctx.save_for_backward(*da, *db)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        da, db = saved[:n], saved[n:]
+        dev = da[0].device
+        ga = [torch.empty(t.shape, dtype=torch.float32, device=dev) for t in da]
+        plan = _l1_plan([t.numel() for t in da], dev, True)
+        _l1_fill_table(plan, (da, db, ga))
+        g = gout.reshape(1).contiguous()
+        L.call("msmc_l1_multi_bwd", L.ptr(plan["table"]), n, L.ptr(plan["sizes"]), L.ptr(plan["ct"]),
+               L.ptr(plan["ci"]), plan["n_chunks"], L.ptr(g))
+        grads = []
+        for t, perm in zip(ga, ctx.perms):
+            inv = [0] * len(perm)
+            for i, d in enumerate(perm):
+                inv[d] = i
+            grads.append(t.permute(inv))     # same shape AND strides as the forward's feature-map view
+        return (None,) + tuple(grads) + (None,) * n
+
+
+def l1_multi(a_list, b_list):
+    """sum over pairs of F.l1_loss(a, b) (mean reduction); b_list is treated as constant"""
+    a_list, b_list = list(a_list), list(b_list)
+    assert len(a_list) == len(b_list) and a_list
+    return _L1MultiFn.apply(len(a_list), *a_list, *[b.detach() for b in b_list])
 
 
 # ------------------------------------------------------------------------------------------- dropout rng

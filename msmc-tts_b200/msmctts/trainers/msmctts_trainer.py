@@ -230,7 +230,12 @@ class VQGANTrainer(BaseTrainer):
                     with torch.no_grad():
                         _, real_feats = disc(target)
             adv = sum(F.mse_loss(s, torch.ones_like(s)) for s in fake_scores)
-            fm = sum(F.l1_loss(a, b) for fa, fb in zip(fake_feats, real_feats) for a, b in zip(fa, fb))
+            if self.reference_schedule or not predict.is_cuda:
+                fm = sum(F.l1_loss(a, b) for fa, fb in zip(fake_feats, real_feats) for a, b in zip(fa, fb))
+            else:
+                # the 55 L1 terms in one multi-tensor kernel (real features carry no graph in this schedule)
+                from msmctts._b200.functional import l1_multi
+                fm = l1_multi([a for fa in fake_feats for a in fa], [b for fb in real_feats for b in fb])
             scale = self.lambda_fm if self.lambda_fm != "auto" else (g_loss / fm).detach()
             adv_loss = adv + fm * scale
             g_loss = g_loss + adv_loss

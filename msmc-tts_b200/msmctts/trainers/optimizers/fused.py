@@ -25,6 +25,7 @@ class FusedAdam(torch.optim.Optimizer):
                         differentiable=False)
         super().__init__(params, defaults)
         self._plans = {}
+        self._graph_plans = []
 
     # ---------------------------------------------------------------------------------------------- state
     def _ensure_state(self, group):
@@ -65,10 +66,15 @@ class FusedAdam(torch.optim.Optimizer):
 
     # ----------------------------------------------------------------------------------------------- step
     def _plan(self, gi, active):
-        """static per (group, set of parameters with gradients): sizes and chunk map on the device"""
+        """static per (group, set of parameters with gradients): sizes and chunk map on the device.  A plan used
+        inside a CUDA-graph capture gets PRIVATE pointer-table staging (spares allocated by an earlier eager step):
+        the captured H2D copy re-reads the pinned buffer on every replay, so eager steps must not overwrite it."""
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
         key = (gi, tuple(active))
         plan = self._plans.get(key)
         if plan is None:
+            if capturing:
+                raise L.MsmcError("FusedAdam: run one eager step before capturing a CUDA graph")
             group = self.param_groups[gi]
             ps = [group["params"][i] for i in active]
             dev = ps[0].device
@@ -79,15 +85,25 @@ class FusedAdam(torch.optim.Optimizer):
                 for c in range((n + chunk - 1) // chunk):
                     ct.append(t)
                     ci.append(c)
+
+            def staging():
+                return (torch.empty(4 * len(ps), dtype=torch.int64).pin_memory(),
+                        torch.empty(4 * len(ps), dtype=torch.int64, device=dev))
+            host, table = staging()
             plan = {
                 "sizes": torch.tensor(sizes, dtype=torch.int64, device=dev),
                 "ct": torch.tensor(ct, dtype=torch.int32, device=dev),
                 "ci": torch.tensor(ci, dtype=torch.int32, device=dev),
-                "host": torch.empty(4 * len(ps), dtype=torch.int64).pin_memory(),
-                "table": torch.empty(4 * len(ps), dtype=torch.int64, device=dev),
-                "n_chunks": len(ct),
+                "host": host, "table": table, "n_chunks": len(ct),
+                "spares": [staging() for _ in range(2)],
             }
             self._plans[key] = plan
+        if capturing:
+            if not plan["spares"]:
+                raise L.MsmcError("FusedAdam: no private staging buffer left for another CUDA-graph capture")
+            host, table = plan["spares"].pop()
+            plan = dict(plan, host=host, table=table, spares=None)
+            self._graph_plans.append(plan)
         return plan
 
     @torch.no_grad()

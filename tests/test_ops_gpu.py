@@ -427,3 +427,40 @@ def test_library_fails_loudly_without_cuda_tensor():
     from msmctts._b200.lib import MsmcError
     with pytest.raises(MsmcError):
         Fn.linear_cl(torch.randn(2, 3, 8), torch.randn(4, 8))
+
+
+def test_l1_multi_matches_sum_of_l1_losses():
+    """fused feature-matching loss == sum of F.l1_loss over the pairs (reference trainers/msmctts_trainer.py:186-190),
+    value and gradients, on permuted channels-last views like the discriminator's feature maps, an odd-sized tensor
+    and one pair with exact zeros (sign(0) = 0).  Tolerance 2e-6 relative: summation order only."""
+    from msmctts._b200 import functional as Fn
+    dev = _dev()
+    torch.manual_seed(3)
+    shapes = [(4, 9, 7, 16), (2, 33, 5, 32), (3, 1, 40001, 1), (2, 5, 3, 8)]
+    a_cpu, b_cpu = [], []
+    for i, s in enumerate(shapes):
+        a = torch.randn(s)
+        b = torch.randn(s)
+        if i == 3:
+            b[0] = a[0]
+        a_cpu.append(a)
+        b_cpu.append(b)
+    # device tensors are (B, H, W, C) buffers seen through the reference's (B, C, H, W) layout
+    a_dev = [a.to(dev).requires_grad_(True) for a in a_cpu]
+    b_dev = [b.to(dev) for b in b_cpu]
+    loss = Fn.l1_multi([a.permute(0, 3, 1, 2) for a in a_dev], [b.permute(0, 3, 1, 2) for b in b_dev])
+    (loss * 1.7).backward()
+    a_ref = [a.clone().requires_grad_(True) for a in a_cpu]
+    ref = sum(F.l1_loss(a.permute(0, 3, 1, 2), b.permute(0, 3, 1, 2)) for a, b in zip(a_ref, b_cpu))
+    (ref * 1.7).backward()
+    assert abs(float(loss) - float(ref)) <= 2e-6 * abs(float(ref))
+    for x, y in zip(a_dev, a_ref):
+        close(x.grad, y.grad, tol=1e-6, msg="l1_multi grad")
+    # non-dense input (a strided slice) takes the copy path
+    z = torch.randn(2, 6, 10, device=dev, requires_grad=True)
+    w = torch.randn(2, 6, 5, device=dev)
+    l2 = Fn.l1_multi([z[:, :, ::2]], [w])
+    l2.backward()
+    zr = z.detach().cpu().requires_grad_(True)
+    F.l1_loss(zr[:, :, ::2], w.cpu()).backward()
+    close(z.grad, zr.grad, tol=1e-6, msg="l1_multi strided grad")
