@@ -329,13 +329,15 @@ def run_b200(args, rank, world, local_rank):
     h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
 
     roof, families, vq = None, None, None
+    # ---- roofline pass: CUDA events around every C-ABI call of two more EAGER steps (same stream).  Every rank runs
+    # the steps (they contain the gradient all-reduce); rank 0 alone records and reports.
+    trainer.use_cuda_graph = False
     if rank == 0:
-        # ---- roofline pass: CUDA events around every C-ABI call of two more EAGER steps (same stream)
-        trainer.use_cuda_graph = False
         L.profile_begin()
-        for i in range(2):
-            step_resident(100 + i)
-        torch.cuda.synchronize()
+    for i in range(2):
+        step_resident(100 + i)
+    torch.cuda.synchronize()
+    if rank == 0:
         prof = L.profile_end()
         fam = {}
         for name, meta, e0, e1 in prof:

@@ -20,17 +20,17 @@ namespace msmc {
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// element-wise operand transforms (msmc_xform)
+// element-wise operand transforms (msmc_xform).  `xf` is uniform per launch.  Written without a `switch`: the jump
+// table (BRX, one indirect branch per element) showed up as ~1M indirect branches per launch in the weight-gradient
+// producers (profiles/r01_ncu_full_wgrad128_summary.txt).  Every piece-wise linear transform is one select:
+//   result = (sel > 0 ? v : s * v),  sel = v (LRELU, RELU, NONE) or aux (MUL_DLRELU, MUL_DRELU),
+//   s = slope (leaky), 0 (relu) or 1 (identity); the compiler hoists sel / s selection out of the element loops.
 __device__ __forceinline__ float apply_xf(int xf, float slope, float v, float aux) {
-  switch (xf) {
-    case MSMC_XF_LRELU: return v > 0.f ? v : slope * v;
-    case MSMC_XF_RELU: return fmaxf(v, 0.f);
-    case MSMC_XF_TANH: return tanhf(v);
-    case MSMC_XF_MUL_DLRELU: return aux > 0.f ? v : slope * v;
-    case MSMC_XF_MUL_DRELU: return aux > 0.f ? v : 0.f;
-    case MSMC_XF_MUL_DTANH: return v * (1.f - aux * aux);
-    default: return v;
-  }
+  if (xf == MSMC_XF_TANH) return tanhf(v);
+  if (xf == MSMC_XF_MUL_DTANH) return v * (1.f - aux * aux);
+  const float sel = (xf >= MSMC_XF_MUL_DLRELU) ? aux : v;
+  const float s = (xf == MSMC_XF_NONE) ? 1.f : ((xf == MSMC_XF_LRELU || xf == MSMC_XF_MUL_DLRELU) ? slope : 0.f);
+  return sel > 0.f ? v : s * v;
 }
 __host__ __device__ inline bool xf_needs_aux(int xf) { return xf >= MSMC_XF_MUL_DLRELU; }
 

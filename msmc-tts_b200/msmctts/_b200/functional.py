@@ -57,6 +57,10 @@ def _weight_image(w, T, Cs, Cd, role, split, bn):
         cache = {}
         w._msmc_img = cache
     key = (role, split, bn)
+    owner = getattr(w, "_msmc_owner", None)
+    if owner is not None and not PREFETCHING[0]:
+        keys = owner.__dict__.setdefault("_msmc_img_keys", set())
+        keys.add((T, Cs, Cd, role, split, bn))
     img = cache.get(key)
     if img is None:
         n = L.load().msmc_weight_image_elems(T, Cs, Cd, role, split, bn)
@@ -347,16 +351,24 @@ def conv_cl(x, w, bias=None, residual=None, *, kernel=(1, 1), stride=(1, 1), dil
     return _ConvFn.apply(x, w, bias, residual, cfg)
 
 
-def linear_cl(x, weight, bias=None, residual=None, post="none", pre_slope=None):
-    """x (..., Ci) @ weight(Co, Ci)^T + bias, weight consumed in torch's native nn.Linear / 1x1-conv layout."""
+def linear_cl(x, weight, bias=None, residual=None, post="none", pre_slope=None, owner=None):
+    """x (..., Ci) @ weight(Co, Ci)^T + bias, weight consumed in torch's native nn.Linear / 1x1-conv layout.
+    `owner` (the layer module) lets the re-laid-out weight be shared / prefetched per parameter version."""
     Ci = x.shape[-1]
     Co = weight.shape[0]
     lead = x.shape[:-1]
     x4 = x.reshape(-1, 1, 1, Ci)
     r4 = residual.reshape(-1, 1, 1, Co) if residual is not None else None
-    if CONV_MATH != "fp32" and Ci % 32 == 0 and x4.shape[0] >= UMMA_MIN_ROWS and weight.requires_grad:
+    umma = CONV_MATH != "fp32" and Ci % 32 == 0 and x4.shape[0] >= UMMA_MIN_ROWS and weight.requires_grad
+    if owner is not None:
+        owner.__dict__["_msmc_lin_umma"] = bool(umma)
+    if umma:
         # tensor-core path wants the GEMM layout [1][Ci][Co]; the re-layout is one tiny launch
-        w_g = prep_conv_weight(weight.reshape(Co, Ci, 1))
+        if owner is not None:
+            from .layers import _prepped
+            w_g = _prepped(owner, weight.reshape(Co, Ci, 1), None)
+        else:
+            w_g = prep_conv_weight(weight.reshape(Co, Ci, 1))
         y = conv_cl(x4, w_g, bias, r4, post=post, pre_slope=pre_slope)
     else:
         y = conv_cl(x4, weight.reshape(Co, Ci), bias, r4, wstr=(0, 0, 1, Ci), out_channels=Co, post=post,
@@ -480,6 +492,20 @@ def run_branches(fns):
     for s in pool[:len(fns)]:
         main.wait_stream(s)
     return outs
+
+
+# weight prefetch (layers.prefetch_weights): side stream per consumer stream, re-entrancy flag
+PREFETCH_WEIGHTS = os.environ.get("MSMC_PREFETCH_WEIGHTS", "1") != "0"
+PREFETCHING = [False]
+_prefetch_streams = {}
+
+
+def prefetch_stream(cur):
+    key = (cur.device.index, cur.cuda_stream)
+    s = _prefetch_streams.get(key)
+    if s is None:
+        s = _prefetch_streams[key] = torch.cuda.Stream(device=cur.device)
+    return s
 
 
 # id of the trainer step in flight (0 = none): layers share one re-parametrised weight per parameter version inside it

@@ -1,6 +1,7 @@
 """Parameter containers whose names/shapes match torch.nn (and old-style torch.nn.utils.weight_norm) modules so the
 reference's checkpoints load unchanged, with forwards that run on the channels-last sm_100a kernels."""
 import math
+import warnings
 
 import torch
 from torch import nn
@@ -24,7 +25,9 @@ def _prepped(mod, v, g, transposed=False, swap_taps=False):
 
     The discriminator runs twice per phase (fake, real) on the same weights: the re-parametrisation, its
     tensor-core operand images and its backward then run once per parameter version instead of once per call.
-    The entry is dropped as soon as a backward pass has consumed it (its saved tensors are gone by then)."""
+    The entry is dropped as soon as a backward pass has consumed it (its saved tensors are gone by then).
+    An entry produced by `prefetch_weights` carries the event recorded after its kernels on the prefetch stream;
+    every consumer stream waits on it."""
     scope = Fn.PREP_SCOPE[0]
     if scope == 0:       # sharing is only safe inside a trainer step (nobody edits .data behind autograd's back there)
         return Fn.prep_conv_weight(v.transpose(2, 3) if swap_taps else v, g, transposed=transposed)
@@ -32,18 +35,71 @@ def _prepped(mod, v, g, transposed=False, swap_taps=False):
     key = (scope, v._version, -1 if g is None else g._version, grad, v.data_ptr())
     hit = mod.__dict__.get("_msmc_prep")
     if hit is not None and hit[0] == key and not hit[2]["spent"]:
+        ev = hit[2].get("event")
+        if ev is not None and not Fn.PREFETCHING[0]:
+            torch.cuda.current_stream().wait_event(ev)
         return hit[1]
-    token = {"spent": False}
+    token = {"spent": False, "event": None}
     w = Fn.prep_conv_weight(v.transpose(2, 3) if swap_taps else v, g, transposed=transposed, token=token)
+    w._msmc_owner = mod          # lets _weight_image remember which operand images this layer asks for
     mod.__dict__["_msmc_prep"] = (key, w, token)
     return w
+
+
+# prefetched weights are re-parametrised on the prefetch stream, so their backward nodes run there too while the
+# AccumulateGrad nodes stay on the stream that created them; autograd orders the two with events (correct, and the
+# step is captured on a non-default stream), but says so once per backward call
+warnings.filterwarnings("ignore", message="The AccumulateGrad node's stream does not match")
+
+
+def prefetch_weights(root):
+    """Re-parametrise every conv / linear weight under `root` (and rebuild the tensor-core operand images each
+    layer used on its previous call) on a dedicated side stream, in module order, ahead of the forward pass.
+
+    One step runs ~700 of these 3-10 us launches; issued inline they sit on the critical path in front of every
+    conv.  Here they overlap the convolutions of earlier layers: each layer's entry carries an event and the
+    consuming stream waits only for its own weight.  Must be called inside a `prep_scope()`; returns the side
+    stream (the caller joins it before the step ends) or None when there is nothing to do."""
+    if Fn.PREP_SCOPE[0] == 0 or not Fn.PREFETCH_WEIGHTS:
+        return None
+    mods = [m for m in root.modules() if hasattr(m, "_prep_spec")]
+    if not mods or not next(root.parameters()).is_cuda:
+        return None
+    cur = torch.cuda.current_stream()
+    side = Fn.prefetch_stream(cur)
+    side.wait_stream(cur)
+    Fn.PREFETCHING[0] = True
+    try:
+        with torch.cuda.stream(side):
+            for m in mods:
+                spec = m._prep_spec()
+                if spec is None:
+                    continue
+                w = _prepped(m, *spec)
+                token = m.__dict__["_msmc_prep"][2]
+                if token.get("event") is not None or token.get("inline"):
+                    continue                       # already prepared in this scope
+                for key in m.__dict__.get("_msmc_img_keys", ()):
+                    Fn._weight_image(w, *key)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                token["event"] = ev
+    finally:
+        Fn.PREFETCHING[0] = False
+    return side
 
 
 class Linear(nn.Linear):
     """nn.Linear parameters; forward = msmc_conv_forward with the weight consumed in its native (Co, Ci) layout."""
 
+    def _prep_spec(self):
+        # only when the previous call took the tensor-core path (it needs the GEMM-layout copy of the weight)
+        if not self.__dict__.get("_msmc_lin_umma") or not self.weight.requires_grad:
+            return None
+        return (self.weight.reshape(self.out_features, self.in_features, 1), None)
+
     def forward(self, x, post="none", residual=None):
-        return Fn.linear_cl(x, self.weight, self.bias, residual=residual, post=post)
+        return Fn.linear_cl(x, self.weight, self.bias, residual=residual, post=post, owner=self)
 
 
 class Conv1d(nn.Module):
@@ -60,11 +116,19 @@ class Conv1d(nn.Module):
     def gemm_weight(self):
         return self.weight, None
 
+    def _prep_spec(self):
+        v, g = self.gemm_weight()
+        if self.kernel_size == 1 and g is None:
+            if not self.__dict__.get("_msmc_lin_umma") or not v.requires_grad:
+                return None
+            return (v.reshape(v.shape[0], v.shape[1], 1), None)
+        return (v, g)
+
     def forward(self, x, pre_slope=None, post="none", residual=None):
         B, L, _ = x.shape
         v, g = self.gemm_weight()
         if self.kernel_size == 1 and g is None:
-            return Fn.linear_cl(x, v, self.bias, residual=residual, post=post, pre_slope=pre_slope)
+            return Fn.linear_cl(x, v, self.bias, residual=residual, post=post, pre_slope=pre_slope, owner=self)
         w = _prepped(self, v, g)
         r4 = residual.unsqueeze(1) if residual is not None else None
         y = Fn.conv_cl(x.unsqueeze(1), w, self.bias, r4, kernel=(1, self.kernel_size), stride=(1, self.stride),
@@ -98,6 +162,9 @@ class WNConvTranspose1d(nn.Module):
         self.weight_g = nn.Parameter(v.norm(2, dim=(1, 2), keepdim=True))
         self.weight_v = nn.Parameter(v)
 
+    def _prep_spec(self):
+        return (self.weight_v, self.weight_g, True)
+
     def forward(self, x, pre_slope=None):
         w = _prepped(self, self.weight_v, self.weight_g, transposed=True)
         y = Fn.conv_cl(x.unsqueeze(1), w, self.bias, kernel=(1, self.kernel_size), stride=(1, self.stride),
@@ -119,6 +186,9 @@ class WNConv2d(nn.Module):
         _conv_init(v, self.bias, in_channels * self.kernel_size[0] * self.kernel_size[1])
         self.weight_g = nn.Parameter(v.norm(2, dim=(1, 2, 3), keepdim=True))
         self.weight_v = nn.Parameter(v)
+
+    def _prep_spec(self):
+        return (self.weight_v, self.weight_g, False, self.swap_hw)
 
     def forward(self, x, pre_slope=None, post="none"):
         KH, KW = self.kernel_size

@@ -185,6 +185,13 @@ class VQGANTrainer(BaseTrainer):
         if mel.is_cuda:
             from msmctts._b200.functional import DeviceRng
             DeviceRng.advance(mel.device)      # device-side seed bump: a graph replay draws fresh dropout masks
+        prefetch = None
+        if mel.is_cuda and not self.reference_schedule:
+            # weight re-parametrisation + operand images of every layer run ahead of the forward on a side stream
+            from msmctts._b200.layers import prefetch_weights
+            prefetch = prefetch_weights(ae)
+            if gan and not warmup and disc is not None:
+                prefetch_weights(disc)
         if warmup:
             output = ae(mel, mel_length, warmup=True)
         else:
@@ -226,6 +233,8 @@ class VQGANTrainer(BaseTrainer):
                 _, real_feats = disc(target)
             else:
                 with _frozen(disc):         # D is a fixed function here: data gradients only, no weight gradients
+                    if prefetch is not None:
+                        prefetch_weights(disc)      # D was just updated: new parameter versions
                     fake_scores, fake_feats = disc(predict)
                     with torch.no_grad():
                         _, real_feats = disc(target)
@@ -245,6 +254,8 @@ class VQGANTrainer(BaseTrainer):
         self.backward(g_loss, "autoencoder", inputs=only)
         nn.utils.clip_grad_norm_(self.model.autoencoder.parameters(), self.grad_clip_thresh)
         self.optimizer.step(["autoencoder"])
+        if prefetch is not None:
+            torch.cuda.current_stream().wait_stream(prefetch)      # join the side stream (graph capture needs it)
         return {"loss": {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}}
 
 
