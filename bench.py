@@ -388,7 +388,7 @@ def run_b200(args, rank, world, local_rank):
                          "warm-up (%.1f s/step); %d torch threads = fastest of a sweep up to the host's %d logical "
                          "CPUs" % (CPU_SAMPLE_B, dt, threads, ncpu)}
     if rank == 0:
-        print(json.dumps({
+        line = json.dumps({
             "metric": "mel-frames/sec MSMC-VQ-GAN train step", "value": value, "unit": "mel-frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -402,10 +402,16 @@ def run_b200(args, rank, world, local_rank):
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
             "cuda_graph": not args.no_graph,
-            "roofline": roof, "kernel_families": families, "vq_argmin": vq, "cpu_baseline": cpu}))
+            "roofline": roof, "kernel_families": families, "vq_argmin": vq, "cpu_baseline": cpu})
+        print(line, flush=True)
     if distributed:
-        dist.barrier()
-        dist.destroy_process_group()
+        # Leave without tearing the communicator down: destroy_process_group() after CUDA-graph-captured NCCL
+        # all-reduces never returned on the 2-GPU box (the JSON line was already out; the launcher then sat until its
+        # timeout).  All device work of this rank is complete and the result is printed, so exit the process directly.
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
