@@ -1069,10 +1069,18 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
       float acc[16];
       tmem_ld16(taddr + (uint32_t)c0, acc);
       if (rb_ok) {
+        if (n0 + c0 + 16 <= g.Cd && (g.Cd & 3) == 0) {
+          // (the workspace is 256-byte aligned and every partial slab is a multiple of Cd floats long)
+          float* out = part + krow * g.Cd + n0 + c0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < g.Cd) part[krow * g.Cd + n] = acc[j];
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(out + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < g.Cd) part[krow * g.Cd + n] = acc[j];
+          }
         }
       }
     }

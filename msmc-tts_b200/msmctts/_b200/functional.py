@@ -479,7 +479,7 @@ def run_branches(fns):
     main = torch.cuda.current_stream()
     pool = _side_streams.setdefault(main.device, [])
     while len(pool) < len(fns):
-        pool.append(torch.cuda.Stream(device=main.device))
+        pool.append(torch.cuda.Stream(device=main.device, priority=MAIN_PRIORITY))
     outs = []
     _in_branch[0] = True
     try:
@@ -497,6 +497,10 @@ def run_branches(fns):
 # weight prefetch (layers.prefetch_weights): side stream per consumer stream, re-entrancy flag
 PREFETCH_WEIGHTS = os.environ.get("MSMC_PREFETCH_WEIGHTS", "1") != "0"
 PREFETCHING = [False]
+# stream priorities (lower = more urgent): critical-path streams (graph capture stream, sub-network branches) vs the
+# weight-gradient side streams (always 0, the least urgent) vs the prefetch stream
+MAIN_PRIORITY = int(os.environ.get("MSMC_MAIN_PRIORITY", "0"))
+PREFETCH_PRIORITY = int(os.environ.get("MSMC_PREFETCH_PRIORITY", str(MAIN_PRIORITY - 1)))
 _prefetch_streams = {}
 
 
@@ -504,7 +508,9 @@ def prefetch_stream(cur):
     key = (cur.device.index, cur.cuda_stream)
     s = _prefetch_streams.get(key)
     if s is None:
-        s = _prefetch_streams[key] = torch.cuda.Stream(device=cur.device)
+        # high priority: the prefetched kernels are tiny and the forward waits on them, so when both are runnable
+        # the block scheduler should take them before the next wave of a long convolution
+        s = _prefetch_streams[key] = torch.cuda.Stream(device=cur.device, priority=PREFETCH_PRIORITY)
     return s
 
 

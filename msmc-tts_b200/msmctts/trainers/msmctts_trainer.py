@@ -165,7 +165,8 @@ class VQGANTrainer(BaseTrainer):
         if "graph" not in st:
             self.optimizer.zero_grad()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            from msmctts._b200.functional import MAIN_PRIORITY
+            with torch.cuda.graph(graph, stream=torch.cuda.Stream(priority=MAIN_PRIORITY)):
                 st["out"] = self._step(*st["inp"], warmup=warmup, gan=gan)
             st["graph"] = graph
         st["graph"].replay()
