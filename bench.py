@@ -332,6 +332,10 @@ def run_b200(args, rank, world, local_rank):
     # ---- roofline pass: CUDA events around every C-ABI call of two more EAGER steps (same stream).  Every rank runs
     # the steps (they contain the gradient all-reduce); rank 0 alone records and reports.
     trainer.use_cuda_graph = False
+    # one stream for this pass: with the branch / weight-gradient / prefetch side streams on, the time between two
+    # events on one stream would include other streams' kernels sharing the GPU
+    from msmctts._b200 import functional as Fn
+    Fn.BRANCH_STREAMS = Fn.WGRAD_STREAM = Fn.PREFETCH_WEIGHTS = False
     if rank == 0:
         L.profile_begin()
     for i in range(2):

@@ -188,6 +188,10 @@ int msmc_spec_magnitude_bwd(const float* gmag, const float* spec, const float* m
 int msmc_mel_double_fwd(const float* mel, float* out, int64_t n, float ref_db, float min_db, void* stream);
 int msmc_mel_double_bwd(const float* gout, const float* mel, float* gmel, int64_t n, float ref_db,
                         float min_db, void* stream);
+/* out[i] = xf(v[i], aux[i]) for one msmc_xform (pointers 16-byte aligned).  The conv backward uses it to form the
+ * pre-activation gradient g * act'(y) of a fused output activation once (reference: autograd of F.leaky_relu /
+ * F.relu / torch.tanh after each conv, e.g. discriminator.py:41-47, transformer.py:361) */
+int msmc_xform_apply(const float* v, const float* aux, float* out, int64_t n, int32_t xf, float slope, void* stream);
 /* log-compression of MelLoss: out = log(max(x, clip)) and its backward */
 int msmc_log_clamp_fwd(const float* x, float* y, int64_t n, float clip, void* stream);
 int msmc_log_clamp_bwd(const float* gy, const float* x, float* gx, int64_t n, float clip, void* stream);

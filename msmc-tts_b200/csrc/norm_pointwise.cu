@@ -214,6 +214,25 @@ __global__ void mel_double_bwd_kernel(const float* __restrict__ gout, const floa
   }
 }
 
+// out = xf(v, aux): one vectorised pass.  Used by the conv backward to materialise the pre-activation gradient
+// g * act'(y) ONCE, so that the data-gradient and the weight-gradient kernels both read a plain operand (their
+// aux-reading producer variants were 2-4x slower than the plain ones: profiles/r01 launch lists).
+__global__ void __launch_bounds__(256) xform_apply_kernel(const float* __restrict__ v, const float* __restrict__ aux,
+                                                          float* __restrict__ out, int64_t n, int xf, float slope) {
+  const int64_t n4 = n >> 2;
+  const bool need_aux = xf_needs_aux(xf);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(v) + e);
+    const float4 a = need_aux ? __ldg(reinterpret_cast<const float4*>(aux) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(out)[e] = make_float4(apply_xf(xf, slope, x.x, a.x), apply_xf(xf, slope, x.y, a.y),
+                                                    apply_xf(xf, slope, x.z, a.z), apply_xf(xf, slope, x.w, a.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t e = (n4 << 2) + threadIdx.x;
+    out[e] = apply_xf(xf, slope, v[e], need_aux ? aux[e] : 0.f);
+  }
+}
+
 __global__ void log_clamp_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float clip) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x)
@@ -387,6 +406,15 @@ extern "C" int msmc_mel_double_bwd(const float* gout, const float* mel, float* g
                                    float min_db, void* stream) {
   MSMC_REQUIRE(gout && mel && gmel && n > 0 && min_db < 0.f);
   mel_double_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(gout, mel, gmel, n, ref_db, min_db);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+extern "C" int msmc_xform_apply(const float* v, const float* aux, float* out, int64_t n, int32_t xf, float slope,
+                                void* stream) {
+  MSMC_REQUIRE(v && out && n > 0 && xf >= MSMC_XF_NONE && xf <= MSMC_XF_MUL_DTANH);
+  MSMC_REQUIRE(!xf_needs_aux(xf) || aux);
+  MSMC_REQUIRE(((reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(aux)) & 15) == 0);
+  xform_apply_kernel<<<ew_blocks((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(v, aux, out, n, xf, slope);
   MSMC_CHECK_LAUNCH();
   return MSMC_OK;
 }

@@ -65,6 +65,7 @@ SIGNATURES = {
     "msmc_spec_magnitude_bwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _F, _I32, _P]),
     "msmc_mel_double_fwd": (C.c_int, [_P, _P, _I64, _F, _F, _P]),
     "msmc_mel_double_bwd": (C.c_int, [_P, _P, _P, _I64, _F, _F, _P]),
+    "msmc_xform_apply": (C.c_int, [_P, _P, _P, _I64, _I32, _F, _P]),
     "msmc_log_clamp_fwd": (C.c_int, [_P, _P, _I64, _F, _P]),
     "msmc_log_clamp_bwd": (C.c_int, [_P, _P, _P, _I64, _F, _P]),
     "msmc_adam_chunk_elems": (C.c_int, []),

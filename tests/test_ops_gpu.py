@@ -464,3 +464,23 @@ def test_l1_multi_matches_sum_of_l1_losses():
     zr = z.detach().cpu().requires_grad_(True)
     F.l1_loss(zr[:, :, ::2], w.cpu()).backward()
     close(z.grad, zr.grad, tol=1e-6, msg="l1_multi strided grad")
+
+
+@pytest.mark.parametrize("xf,slope", [(1, 0.2), (2, 0.0), (3, 0.0), (4, 0.1), (5, 0.0), (6, 0.0)])
+def test_xform_apply(xf, slope):
+    """msmc_xform_apply == the element-wise definition of every msmc_xform (include/msmc_b200.h), odd length"""
+    import ctypes as C
+    from msmctts._b200 import lib as L
+    dev = _dev()
+    torch.manual_seed(xf)
+    n = 4099
+    v = torch.randn(n + 1, device=dev)[:n]          # n not a multiple of 4: exercises the scalar tail
+    aux = torch.randn(n + 1, device=dev)[:n]
+    aux[::7] = 0.0
+    out = torch.empty(n, device=dev)
+    L.call("msmc_xform_apply", L.ptr(v), L.ptr(aux), L.ptr(out), C.c_int64(n), xf, C.c_float(slope))
+    vc, ac = v.cpu(), aux.cpu()
+    ref = {1: torch.where(vc > 0, vc, slope * vc), 2: vc.clamp(min=0), 3: torch.tanh(vc),
+           4: torch.where(ac > 0, vc, slope * vc), 5: torch.where(ac > 0, vc, torch.zeros_like(vc)),
+           6: vc * (1 - ac * ac)}[xf]
+    close(out, ref, tol=2e-6, msg="xform %d" % xf)
