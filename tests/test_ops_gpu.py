@@ -186,7 +186,9 @@ def test_conv_swapped_spatial_axes_matches_reference_layout():
 
 
 # ------------------------------------------------------------------------------------------------------- VQ
-@pytest.mark.parametrize("heads,K,n", [(4, 64, 3840), (4, 256, 960), (1, 64, 128), (2, 32, 48), (4, 100, 257)])
+# (4, K in {64,128,256}) take the bulk-staged kernel (4 rows per warp; 8 at n >= 18944), the rest the generic one
+@pytest.mark.parametrize("heads,K,n", [(4, 64, 3840), (4, 256, 960), (1, 64, 128), (2, 32, 48), (4, 100, 257),
+                                       (4, 128, 3841), (4, 256, 20011), (4, 64, 19999), (4, 256, 7)])
 def test_vq_search_bit_exact_vs_c_oracle(heads, K, n):
     from msmctts._b200 import functional as Fn
     from oracle import vq as OV
