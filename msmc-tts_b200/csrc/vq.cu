@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <cooperative_groups.h>
 
 namespace msmc {
 namespace {
@@ -142,80 +143,91 @@ vq_search_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Search kernel, bulk-staged variant (K == padded width, i.e. K in {32, 64, 128, 256, 512}).
-// The generic kernel above spends most of its time at the training shape (3840 / 960 rows, 4 heads, K = 256) copying
-// each head's 64 KB codebook into shared memory with scalar loads -- 4 x 64 KB per CTA for 32 rows of work.  Here the
-// codebook of head h+1 is fetched by ONE cp.async.bulk (TMA unit, no registers, no issue slots) into the second half
-// of a double buffer while head h is being scored; completion is an mbarrier transaction count.  R rows per warp:
-// 4 at small N (more CTAs), 8 at large N (one LDS.128 feeds 32 FMAs, the loop becomes FP32-FMA bound).
-// Arithmetic and its order are IDENTICAL to the generic kernel (and to oracle/vq_oracle.c): indices stay bit-exact.
+// Search kernel, cluster variant (dim 64, K == padded width: K in {64, 128, 256}; n_heads <= 8).
+//
+// The generic kernel above walks the heads one after the other inside every CTA and, at the training shape
+// (3840 / 960 rows, 4 heads, K = 256), spends most of its time copying four 64 KB codebooks into shared memory with
+// scalar loads for 32 rows of work.  Here
+//   * grid = (row blocks, heads) with the CTAs of one row block forming a THREAD-BLOCK CLUSTER (cluster dim y =
+//     n_heads): the heads of a row block are scored concurrently on neighbouring SMs;
+//   * each CTA fetches its ONE codebook with a single cp.async.bulk (TMA unit; completion = mbarrier transaction
+//     count) and keeps it for all of its row passes;
+//   * the commitment term diff = mean_h (q_h - z_h)^2 needs the heads summed in head order (python `sum(diffs)`):
+//     every CTA leaves its per-row squares in shared memory, the cluster synchronises, and each CTA combines a slice
+//     of the rows by reading the other CTAs' tiles through DISTRIBUTED SHARED MEMORY in head order -- no global
+//     read-modify-write between heads, and the fp32 sum is bit-identical to the sequential one.
+// R rows per warp: 4 at small N (more CTAs), 8 with 16 warps at large N (one LDS.128 feeds 32 FMAs).
+// Distances, their fma order and the tie rule are IDENTICAL to the generic kernel and to oracle/vq_oracle.c.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t vq_smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-template <int DIM, int VEC, int KQ, int R>
-__global__ void __launch_bounds__(VQ_WARPS * 32)
-vq_search_bulk_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restrict__ embed,
-                      float* __restrict__ quant_raw, float* __restrict__ quant_st, float* __restrict__ diff,
-                      int64_t* __restrict__ idx, int n_rows, int n_heads, int rows_per_cta) {
-  extern __shared__ __align__(128) float smem[];
+template <int VEC, int KQ, int R, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+vq_search_cluster_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restrict__ embed,
+                         float* __restrict__ quant_raw, float* __restrict__ quant_st, float* __restrict__ diff,
+                         int64_t* __restrict__ idx, int n_rows, int rows_per_cta) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  constexpr int DIM = 64;
   constexpr int KP = 32 * VEC * KQ;      // == K
+  constexpr int RPP = WARPS * R;         // rows per pass
   constexpr uint32_t CB_BYTES = (uint32_t)DIM * KP * sizeof(float);
-  float* ee = smem + 2 * (size_t)DIM * KP;                 // [KP]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ee + KP);   // [2]
+  constexpr int DPL = DIM / 32;
+  extern __shared__ __align__(128) float smem[];
+  float* cb = smem;                                   // [DIM][KP]
+  float* ee = cb + (size_t)DIM * KP;                  // [KP]
+  float* dvs = ee + KP;                               // [2][RPP][DIM]   per-row (q - z)^2 of THIS head
+  uint64_t* bar = reinterpret_cast<uint64_t*>(dvs + 2 * RPP * DIM);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_heads = gridDim.y;
+  const int h = blockIdx.y;                           // == rank in the cluster (cluster = all heads of a row block)
   const int row_beg = blockIdx.x * rows_per_cta;
   const int row_end = min(n_rows, row_beg + rows_per_cta);
   const float inv_heads = 1.f / (float)n_heads;
-  constexpr int DPL = DIM / 32;  // dims per lane
 
-  auto fetch = [&](int h) {      // one elected thread: whole codebook of head h -> buffer h & 1
-    const uint32_t bar = vq_smem_u32(&bars[h & 1]);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(CB_BYTES) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     vq_smem_u32(smem + (size_t)(h & 1) * DIM * KP)),
-                 "l"(embed + (size_t)h * DIM * KP), "r"(CB_BYTES), "r"(bar)
-                 : "memory");
-  };
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(vq_smem_u32(&bars[0])) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(vq_smem_u32(&bars[1])) : "memory");
+    const uint32_t b = vq_smem_u32(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    fetch(0);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(CB_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     vq_smem_u32(cb)),
+                 "l"(embed + (size_t)h * DIM * KP), "r"(CB_BYTES), "r"(b)
+                 : "memory");
+  }
+  __syncthreads();
+  {
+    const uint32_t b = vq_smem_u32(bar);
+    uint32_t ok;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(b), "r"(0u)
+          : "memory");
+    } while (!ok);
+  }
+  for (int k = threadIdx.x; k < KP; k += blockDim.x) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < DIM; ++d) { float v = cb[d * KP + k]; s = fmaf(v, v, s); }
+    ee[k] = s;
   }
   __syncthreads();
 
-  for (int h = 0; h < n_heads; ++h) {
-    const float* cb = smem + (size_t)(h & 1) * DIM * KP;   // [DIM][KP]
-    // the other buffer was last read during head h-1, which ended with a __syncthreads
-    if (threadIdx.x == 0 && h + 1 < n_heads) fetch(h + 1);
-    {
-      const uint32_t bar = vq_smem_u32(&bars[h & 1]), parity = (uint32_t)(h >> 1) & 1u;
-      uint32_t ok;
-      do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-      } while (!ok);
-    }
-    for (int k = threadIdx.x; k < KP; k += blockDim.x) {
-      float s = 0.f;
-#pragma unroll 8
-      for (int d = 0; d < DIM; ++d) { float v = cb[d * KP + k]; s = fmaf(v, v, s); }
-      ee[k] = s;
-    }
-    __syncthreads();
-
-    for (int r0 = row_beg + warp * R; r0 < row_end; r0 += VQ_WARPS * R) {
+  int pass = 0;
+  for (int p0 = row_beg; p0 < row_end; p0 += RPP, ++pass) {
+    float* dv = dvs + (size_t)(pass & 1) * RPP * DIM;
+    const int r0 = p0 + warp * R;
+    if (r0 < row_end) {
       float zl[R][DPL];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int row = min(r0 + r, row_end - 1);       // tail rows are recomputed, never stored twice
+        const int row = min(r0 + r, row_end - 1);       // tail rows are recomputed, never stored
         const float* zr = z + (int64_t)row * ld_z + h * DIM;
 #pragma unroll
         for (int j = 0; j < DPL; ++j) zl[r][j] = zr[lane + 32 * j];
@@ -240,11 +252,9 @@ vq_search_bulk_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
             if (VEC == 4) {
               const float4 t = *reinterpret_cast<const float4*>(cr + q * 32 * VEC);
               ev[q * VEC + 0] = t.x; ev[q * VEC + 1] = t.y; ev[q * VEC + 2] = t.z; ev[q * VEC + 3] = t.w;
-            } else if (VEC == 2) {
+            } else {
               const float2 t = *reinterpret_cast<const float2*>(cr + q * 32 * VEC);
               ev[q * VEC + 0] = t.x; ev[q * VEC + 1] = t.y;
-            } else {
-              ev[q * VEC] = cr[q * 32 * VEC];
             }
           }
 #pragma unroll
@@ -286,18 +296,27 @@ vq_search_bulk_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
             quant_raw[o] = q;
             quant_st[o] = x + (q - x);
             const float dq = q - x;
-            const float dv = __fmul_rn(dq, dq);   // no fma contraction with the head sum below (matches the C oracle)
-            float* dp = diff + (int64_t)row * DIM + d;
-            // sum over heads in head order (python `sum(diffs)`), then / n_heads
-            float acc = (h == 0) ? dv : __fadd_rn(*dp, dv);
-            if (h == n_heads - 1) acc *= inv_heads;
-            *dp = acc;
+            dv[(warp * R + r) * DIM + d] = __fmul_rn(dq, dq);   // no fma contraction with the head sum
           }
         }
       }
     }
-    __syncthreads();   // every read of this head's codebook and norms is done
+    // every head's squares of this pass are in place (release / acquire across the cluster)
+    cluster.sync();
+    // combine: this CTA owns the rows ri with ri % n_heads == h; heads are added in head order, then / n_heads
+    const int rows_here = min(RPP, row_end - p0);
+    for (int e = threadIdx.x; e < RPP * DIM; e += blockDim.x) {
+      const int ri = e / DIM, d = e - ri * DIM;
+      if (ri < rows_here && (ri % n_heads) == h) {
+        float acc = *cluster.map_shared_rank(dv + ri * DIM + d, 0);
+        for (int hh = 1; hh < n_heads; ++hh) acc = __fadd_rn(acc, *cluster.map_shared_rank(dv + ri * DIM + d, hh));
+        diff[(int64_t)(p0 + ri) * DIM + d] = acc * inv_heads;
+      }
+    }
+    // dv is double-buffered: buffer (pass & 1) is rewritten in pass + 2, after the cluster.sync of pass + 1, which
+    // every CTA reaches only after finishing the reads above
   }
+  cluster.sync();     // nobody exits while a neighbour may still read its shared memory
 }
 
 // One CTA per (head, codeword): masked count and masked sum of the rows assigned to it, then the EMA.
@@ -487,28 +506,44 @@ extern "C" int msmc_vq_search(const float* z, int64_t ld_z, const float* embed, 
   else { vec = 4; kq = 4; }
   const int kp = 32 * vec * kq;
   cudaStream_t st = (cudaStream_t)stream;
-  static const int use_bulk = [] { const char* e = getenv("MSMC_VQ_BULK"); return e ? atoi(e) : 1; }();
-  if (use_bulk && dim == 64 && n_embed == kp && vec >= 2 && kp <= 256 &&
+  static const int use_cluster = [] { const char* e = getenv("MSMC_VQ_CLUSTER"); return e ? atoi(e) : 1; }();
+  if (use_cluster && dim == 64 && n_embed == kp && vec >= 2 && kp <= 256 && n_heads <= 8 &&
       (reinterpret_cast<uintptr_t>(embed) & 15) == 0) {
-    // bulk-staged double-buffered variant (the training configurations: K = 64 / 128 / 256 per head, dim 64)
-    const size_t bsmem = (2 * (size_t)dim * kp + kp) * sizeof(float) + 2 * sizeof(uint64_t);
-    const bool big = n_rows >= num_sms() * VQ_WARPS * 8 * 2;     // >= two 8-row passes per warp on every SM
-    const int quantum = VQ_WARPS * (big ? 8 : 4);
-    int rows_per_cta = std::max(quantum, (int)ceil_div(n_rows, num_sms()));
-    rows_per_cta = ceil_div(rows_per_cta, quantum) * quantum;
-    const int grid = ceil_div(n_rows, rows_per_cta);
-#define LAUNCH_VQB(V, Q, R_)                                                                                     \
-  do {                                                                                                          \
-    cudaFuncSetAttribute(vq_search_bulk_kernel<64, V, Q, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                         (int)bsmem);                                                                           \
-    vq_search_bulk_kernel<64, V, Q, R_><<<grid, VQ_WARPS * 32, bsmem, st>>>(z, ld_z, embed, quant_raw, quant_st, \
-                                                                            diff, idx, n_rows, n_heads,         \
-                                                                            rows_per_cta);                      \
+    // cluster variant (the training configurations: K = 64 / 128 / 256 per head, dim 64, 1-8 heads)
+    const int sms = num_sms();
+    const bool big = n_rows >= sms * 128;            // enough rows for 16 warps x 8 rows on every SM
+    const int warps = big ? 16 : 8, rpw = big ? 8 : 4;
+    const int rpp = warps * rpw;
+    const size_t csmem = ((size_t)dim * kp + kp + 2 * (size_t)rpp * dim) * sizeof(float) + sizeof(uint64_t);
+    // one wave of clusters: 2 CTAs per SM fit at K <= 256 with 8 warps, 1 with 16
+    const int max_clusters = std::max(1, (big ? sms : 2 * sms) / n_heads);
+    int gx = std::min(ceil_div(n_rows, rpp), max_clusters);
+    int rows_per_cta = ceil_div(ceil_div(n_rows, gx), rpp) * rpp;
+    gx = ceil_div(n_rows, rows_per_cta);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)gx, (unsigned)n_heads, 1);
+    cfg.blockDim = dim3((unsigned)(warps * 32), 1, 1);
+    cfg.dynamicSmemBytes = csmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = (unsigned)n_heads;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#define LAUNCH_VQC(V, Q, R_, W_)                                                                               \
+  do {                                                                                                        \
+    cudaFuncSetAttribute(vq_search_cluster_kernel<V, Q, R_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                         (int)csmem);                                                                         \
+    if (cudaLaunchKernelEx(&cfg, vq_search_cluster_kernel<V, Q, R_, W_>, z, ld_z, embed, quant_raw, quant_st, \
+                           diff, idx, (int)n_rows, rows_per_cta) != cudaSuccess)                              \
+      return MSMC_ERR_LAUNCH;                                                                                 \
   } while (0)
-    if (vec == 2) { if (big) LAUNCH_VQB(2, 1, 8); else LAUNCH_VQB(2, 1, 4); }
-    else if (kq == 1) { if (big) LAUNCH_VQB(4, 1, 8); else LAUNCH_VQB(4, 1, 4); }
-    else { if (big) LAUNCH_VQB(4, 2, 8); else LAUNCH_VQB(4, 2, 4); }
-#undef LAUNCH_VQB
+    if (vec == 2) { if (big) LAUNCH_VQC(2, 1, 8, 16); else LAUNCH_VQC(2, 1, 4, 8); }
+    else if (kq == 1) { if (big) LAUNCH_VQC(4, 1, 8, 16); else LAUNCH_VQC(4, 1, 4, 8); }
+    else { if (big) LAUNCH_VQC(4, 2, 8, 16); else LAUNCH_VQC(4, 2, 4, 8); }
+#undef LAUNCH_VQC
     MSMC_CHECK_LAUNCH();
     return MSMC_OK;
   }

@@ -186,9 +186,11 @@ def test_conv_swapped_spatial_axes_matches_reference_layout():
 
 
 # ------------------------------------------------------------------------------------------------------- VQ
-# (4, K in {64,128,256}) take the bulk-staged kernel (4 rows per warp; 8 at n >= 18944), the rest the generic one
+# dim 64 with K in {64,128,256} takes the cluster kernel (one CTA per head, DSMEM head sum; 8 warps x 4 rows, or
+# 16 warps x 8 rows at n >= 18944), the rest the generic one
 @pytest.mark.parametrize("heads,K,n", [(4, 64, 3840), (4, 256, 960), (1, 64, 128), (2, 32, 48), (4, 100, 257),
-                                       (4, 128, 3841), (4, 256, 20011), (4, 64, 19999), (4, 256, 7)])
+                                       (4, 128, 3841), (4, 256, 20011), (4, 64, 19999), (4, 256, 7),
+                                       (2, 64, 100), (8, 128, 77), (4, 128, 19200)])
 def test_vq_search_bit_exact_vs_c_oracle(heads, K, n):
     from msmctts._b200 import functional as Fn
     from oracle import vq as OV
