@@ -156,15 +156,15 @@ vq_search_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restr
 //     every CTA leaves its per-row squares in shared memory, the cluster synchronises, and each CTA combines a slice
 //     of the rows by reading the other CTAs' tiles through DISTRIBUTED SHARED MEMORY in head order -- no global
 //     read-modify-write between heads, and the fp32 sum is bit-identical to the sequential one.
-// R rows per warp: 4 at small N (more CTAs), 8 with 16 warps at large N (one LDS.128 feeds 32 FMAs).
+// R rows per warp: 4 at small N (more CTAs), 8 at large N (one LDS.128 feeds 32 FMAs); 2 CTAs of 8 warps per SM.
 // Distances, their fma order and the tie rule are IDENTICAL to the generic kernel and to oracle/vq_oracle.c.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t vq_smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-template <int VEC, int KQ, int R, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1)
+template <int VEC, int KQ, int R, int WARPS, int G>
+__global__ void __launch_bounds__(WARPS * 32, 2)
 vq_search_cluster_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restrict__ embed,
                          float* __restrict__ quant_raw, float* __restrict__ quant_st, float* __restrict__ diff,
                          int64_t* __restrict__ idx, int n_rows, int rows_per_cta) {
@@ -178,8 +178,8 @@ vq_search_cluster_kernel(const float* __restrict__ z, int64_t ld_z, const float*
   extern __shared__ __align__(128) float smem[];
   float* cb = smem;                                   // [DIM][KP]
   float* ee = cb + (size_t)DIM * KP;                  // [KP]
-  float* dvs = ee + KP;                               // [2][RPP][DIM]   per-row (q - z)^2 of THIS head
-  uint64_t* bar = reinterpret_cast<uint64_t*>(dvs + 2 * RPP * DIM);
+  float* dvs = ee + KP;                               // [2][G * RPP][DIM]   per-row (q - z)^2 of THIS head
+  uint64_t* bar = reinterpret_cast<uint64_t*>(dvs + 2 * G * RPP * DIM);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_heads = gridDim.y;
   const int h = blockIdx.y;                           // == rank in the cluster (cluster = all heads of a row block)
@@ -219,9 +219,13 @@ vq_search_cluster_kernel(const float* __restrict__ z, int64_t ld_z, const float*
   }
   __syncthreads();
 
+  // passes are grouped G at a time: one cluster barrier + one combine per group (a barrier costs about as much as
+  // scoring 32 rows); the group buffers are double-buffered so that one barrier per group suffices
   int pass = 0;
   for (int p0 = row_beg; p0 < row_end; p0 += RPP, ++pass) {
-    float* dv = dvs + (size_t)(pass & 1) * RPP * DIM;
+    const int grp = pass / G, pig = pass - grp * G;          // group index, pass inside the group
+    float* dvg = dvs + (size_t)(grp & 1) * G * RPP * DIM;    // this group's buffer
+    float* dv = dvg + (size_t)pig * RPP * DIM;
     const int r0 = p0 + warp * R;
     if (r0 < row_end) {
       float zl[R][DPL];
@@ -301,20 +305,25 @@ vq_search_cluster_kernel(const float* __restrict__ z, int64_t ld_z, const float*
         }
       }
     }
-    // every head's squares of this pass are in place (release / acquire across the cluster)
-    cluster.sync();
-    // combine: this CTA owns the rows ri with ri % n_heads == h; heads are added in head order, then / n_heads
-    const int rows_here = min(RPP, row_end - p0);
-    for (int e = threadIdx.x; e < RPP * DIM; e += blockDim.x) {
-      const int ri = e / DIM, d = e - ri * DIM;
-      if (ri < rows_here && (ri % n_heads) == h) {
-        float acc = *cluster.map_shared_rank(dv + ri * DIM + d, 0);
-        for (int hh = 1; hh < n_heads; ++hh) acc = __fadd_rn(acc, *cluster.map_shared_rank(dv + ri * DIM + d, hh));
-        diff[(int64_t)(p0 + ri) * DIM + d] = acc * inv_heads;
+    const bool group_end = (pig == G - 1) || (p0 + RPP >= row_end);
+    if (group_end) {
+      // every head's squares of this group are in place (release / acquire across the cluster)
+      cluster.sync();
+      // combine: this CTA owns the rows ri with ri % n_heads == h; heads are added in head order, then / n_heads
+      const int g0 = p0 - pig * RPP;                        // first row of the group
+      const int rows_here = min((pig + 1) * RPP, row_end - g0);
+      for (int e = threadIdx.x; e < (pig + 1) * RPP * DIM; e += blockDim.x) {
+        const int ri = e / DIM, d = e - ri * DIM;
+        if (ri < rows_here && (ri % n_heads) == h) {
+          float acc = *cluster.map_shared_rank(dvg + ri * DIM + d, 0);
+          for (int hh = 1; hh < n_heads; ++hh)
+            acc = __fadd_rn(acc, *cluster.map_shared_rank(dvg + ri * DIM + d, hh));
+          diff[(int64_t)(g0 + ri) * DIM + d] = acc * inv_heads;
+        }
       }
+      // buffer (grp & 1) is rewritten in group grp + 2, after the cluster.sync of group grp + 1, which every CTA
+      // reaches only after finishing the reads above
     }
-    // dv is double-buffered: buffer (pass & 1) is rewritten in pass + 2, after the cluster.sync of pass + 1, which
-    // every CTA reaches only after finishing the reads above
   }
   cluster.sync();     // nobody exits while a neighbour may still read its shared memory
 }
@@ -511,12 +520,12 @@ extern "C" int msmc_vq_search(const float* z, int64_t ld_z, const float* embed, 
       (reinterpret_cast<uintptr_t>(embed) & 15) == 0) {
     // cluster variant (the training configurations: K = 64 / 128 / 256 per head, dim 64, 1-8 heads)
     const int sms = num_sms();
-    const bool big = n_rows >= sms * 128;            // enough rows for 16 warps x 8 rows on every SM
-    const int warps = big ? 16 : 8, rpw = big ? 8 : 4;
+    const bool big = n_rows >= sms * 128;            // enough rows for 2 CTAs x 8 warps x 8 rows on every SM
+    const int warps = 8, rpw = big ? 8 : 4, grp = big ? 1 : 2;
     const int rpp = warps * rpw;
-    const size_t csmem = ((size_t)dim * kp + kp + 2 * (size_t)rpp * dim) * sizeof(float) + sizeof(uint64_t);
-    // one wave of clusters: 2 CTAs per SM fit at K <= 256 with 8 warps, 1 with 16
-    const int max_clusters = std::max(1, (big ? sms : 2 * sms) / n_heads);
+    const size_t csmem = ((size_t)dim * kp + kp + 2 * (size_t)grp * rpp * dim) * sizeof(float) + sizeof(uint64_t);
+    // one wave of clusters: 2 CTAs per SM (<= 97 KB of shared memory, <= 128 registers x 256 threads each)
+    const int max_clusters = std::max(1, 2 * sms / n_heads);
     int gx = std::min(ceil_div(n_rows, rpp), max_clusters);
     int rows_per_cta = ceil_div(ceil_div(n_rows, gx), rpp) * rpp;
     gx = ceil_div(n_rows, rows_per_cta);
@@ -532,17 +541,17 @@ extern "C" int msmc_vq_search(const float* z, int64_t ld_z, const float* embed, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-#define LAUNCH_VQC(V, Q, R_, W_)                                                                               \
+#define LAUNCH_VQC(V, Q, R_, W_, G_)                                                                             \
   do {                                                                                                        \
-    cudaFuncSetAttribute(vq_search_cluster_kernel<V, Q, R_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    cudaFuncSetAttribute(vq_search_cluster_kernel<V, Q, R_, W_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                          (int)csmem);                                                                         \
-    if (cudaLaunchKernelEx(&cfg, vq_search_cluster_kernel<V, Q, R_, W_>, z, ld_z, embed, quant_raw, quant_st, \
+    if (cudaLaunchKernelEx(&cfg, vq_search_cluster_kernel<V, Q, R_, W_, G_>, z, ld_z, embed, quant_raw, quant_st, \
                            diff, idx, (int)n_rows, rows_per_cta) != cudaSuccess)                              \
       return MSMC_ERR_LAUNCH;                                                                                 \
   } while (0)
-    if (vec == 2) { if (big) LAUNCH_VQC(2, 1, 8, 16); else LAUNCH_VQC(2, 1, 4, 8); }
-    else if (kq == 1) { if (big) LAUNCH_VQC(4, 1, 8, 16); else LAUNCH_VQC(4, 1, 4, 8); }
-    else { if (big) LAUNCH_VQC(4, 2, 8, 16); else LAUNCH_VQC(4, 2, 4, 8); }
+    if (vec == 2) { if (big) LAUNCH_VQC(2, 1, 8, 8, 1); else LAUNCH_VQC(2, 1, 4, 8, 2); }
+    else if (kq == 1) { if (big) LAUNCH_VQC(4, 1, 8, 8, 1); else LAUNCH_VQC(4, 1, 4, 8, 2); }
+    else { if (big) LAUNCH_VQC(4, 2, 8, 8, 1); else LAUNCH_VQC(4, 2, 4, 8, 2); }
 #undef LAUNCH_VQC
     MSMC_CHECK_LAUNCH();
     return MSMC_OK;
