@@ -328,6 +328,162 @@ vq_search_cluster_kernel(const float* __restrict__ z, int64_t ld_z, const float*
   cluster.sync();     // nobody exits while a neighbour may still read its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Search kernel, large-N variant (n_rows >= 128 per SM; K == padded width).  Heads are walked inside the CTA like in
+// the generic kernel -- with thousands of rows per CTA the warps never meet at a barrier inside a head, which hides
+// the row loads and the epilogue better than the per-pass cluster barrier of the variant above (measured: 498 vs
+// 344 GB/s at 2^20 rows) -- but the
+// codebook of head h+1 is fetched by ONE cp.async.bulk (TMA unit, no registers, no issue slots) into the second half
+// of a double buffer while head h is being scored; completion is an mbarrier transaction count.  R rows per warp:
+// 4 at small N (more CTAs), 8 at large N (one LDS.128 feeds 32 FMAs, the loop becomes FP32-FMA bound).
+// Arithmetic and its order are IDENTICAL to the generic kernel (and to oracle/vq_oracle.c): indices stay bit-exact.
+// ------------------------------------------------------------------------------------------------------------
+template <int DIM, int VEC, int KQ, int R>
+__global__ void __launch_bounds__(VQ_WARPS * 32)
+vq_search_bulk_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restrict__ embed,
+                      float* __restrict__ quant_raw, float* __restrict__ quant_st, float* __restrict__ diff,
+                      int64_t* __restrict__ idx, int n_rows, int n_heads, int rows_per_cta) {
+  extern __shared__ __align__(128) float smem[];
+  constexpr int KP = 32 * VEC * KQ;      // == K
+  constexpr uint32_t CB_BYTES = (uint32_t)DIM * KP * sizeof(float);
+  float* ee = smem + 2 * (size_t)DIM * KP;                 // [KP]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ee + KP);   // [2]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_beg = blockIdx.x * rows_per_cta;
+  const int row_end = min(n_rows, row_beg + rows_per_cta);
+  const float inv_heads = 1.f / (float)n_heads;
+  constexpr int DPL = DIM / 32;  // dims per lane
+
+  auto fetch = [&](int h) {      // one elected thread: whole codebook of head h -> buffer h & 1
+    const uint32_t bar = vq_smem_u32(&bars[h & 1]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(CB_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     vq_smem_u32(smem + (size_t)(h & 1) * DIM * KP)),
+                 "l"(embed + (size_t)h * DIM * KP), "r"(CB_BYTES), "r"(bar)
+                 : "memory");
+  };
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(vq_smem_u32(&bars[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(vq_smem_u32(&bars[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fetch(0);
+  }
+  __syncthreads();
+
+  for (int h = 0; h < n_heads; ++h) {
+    const float* cb = smem + (size_t)(h & 1) * DIM * KP;   // [DIM][KP]
+    // the other buffer was last read during head h-1, which ended with a __syncthreads
+    if (threadIdx.x == 0 && h + 1 < n_heads) fetch(h + 1);
+    {
+      const uint32_t bar = vq_smem_u32(&bars[h & 1]), parity = (uint32_t)(h >> 1) & 1u;
+      uint32_t ok;
+      do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+      } while (!ok);
+    }
+    for (int k = threadIdx.x; k < KP; k += blockDim.x) {
+      float s = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < DIM; ++d) { float v = cb[d * KP + k]; s = fmaf(v, v, s); }
+      ee[k] = s;
+    }
+    __syncthreads();
+
+    for (int r0 = row_beg + warp * R; r0 < row_end; r0 += VQ_WARPS * R) {
+      float zl[R][DPL];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int row = min(r0 + r, row_end - 1);       // tail rows are recomputed, never stored twice
+        const float* zr = z + (int64_t)row * ld_z + h * DIM;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) zl[r][j] = zr[lane + 32 * j];
+      }
+      float dot[R][KQ * VEC];
+      float zz[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        zz[r] = 0.f;
+#pragma unroll
+        for (int c = 0; c < KQ * VEC; ++c) dot[r][c] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) {
+#pragma unroll 4
+        for (int dl = 0; dl < 32; ++dl) {
+          // sequential over d = 32*j + dl, identical order to oracle/vq_oracle.c
+          float ev[KQ * VEC];
+          const float* cr = cb + (size_t)(32 * j + dl) * KP + lane * VEC;
+#pragma unroll
+          for (int q = 0; q < KQ; ++q) {
+            if (VEC == 4) {
+              const float4 t = *reinterpret_cast<const float4*>(cr + q * 32 * VEC);
+              ev[q * VEC + 0] = t.x; ev[q * VEC + 1] = t.y; ev[q * VEC + 2] = t.z; ev[q * VEC + 3] = t.w;
+            } else if (VEC == 2) {
+              const float2 t = *reinterpret_cast<const float2*>(cr + q * 32 * VEC);
+              ev[q * VEC + 0] = t.x; ev[q * VEC + 1] = t.y;
+            } else {
+              ev[q * VEC] = cr[q * 32 * VEC];
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float zd = __shfl_sync(0xffffffffu, zl[r][j], dl);
+            zz[r] = fmaf(zd, zd, zz[r]);
+#pragma unroll
+            for (int c = 0; c < KQ * VEC; ++c) dot[r][c] = fmaf(zd, ev[c], dot[r][c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int row = r0 + r;
+        float best = INFINITY;
+        int best_k = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < KQ; ++q)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const int k = q * 32 * VEC + lane * VEC + v;
+            const float dist = (zz[r] - 2.f * dot[r][q * VEC + v]) + ee[k];
+            if (dist < best || (dist == best && k < best_k)) { best = dist; best_k = k; }
+          }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+          if (ob < best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
+        }
+        if (row < row_end) {
+          if (lane == 0) idx[(int64_t)row * n_heads + h] = (int64_t)best_k;
+#pragma unroll
+          for (int j = 0; j < DPL; ++j) {
+            const int d = lane + 32 * j;
+            const float q = cb[d * KP + best_k];
+            const float x = zl[r][j];
+            const int64_t o = (int64_t)row * (n_heads * DIM) + h * DIM + d;
+            quant_raw[o] = q;
+            quant_st[o] = x + (q - x);
+            const float dq = q - x;
+            const float dv = __fmul_rn(dq, dq);   // no fma contraction with the head sum below (matches the C oracle)
+            float* dp = diff + (int64_t)row * DIM + d;
+            // sum over heads in head order (python `sum(diffs)`), then / n_heads
+            float acc = (h == 0) ? dv : __fadd_rn(*dp, dv);
+            if (h == n_heads - 1) acc *= inv_heads;
+            *dp = acc;
+          }
+        }
+      }
+    }
+    __syncthreads();   // every read of this head's codebook and norms is done
+  }
+}
+
 // One CTA per (head, codeword): masked count and masked sum of the rows assigned to it, then the EMA.
 template <int DIM>
 __global__ void __launch_bounds__(256)
@@ -520,8 +676,32 @@ extern "C" int msmc_vq_search(const float* z, int64_t ld_z, const float* embed, 
       (reinterpret_cast<uintptr_t>(embed) & 15) == 0) {
     // cluster variant (the training configurations: K = 64 / 128 / 256 per head, dim 64, 1-8 heads)
     const int sms = num_sms();
-    const bool big = n_rows >= sms * 128;            // enough rows for 2 CTAs x 8 warps x 8 rows on every SM
-    const int warps = 8, rpw = big ? 8 : 4, grp = big ? 1 : 2;
+    if (n_rows >= sms * 128) {
+      // large N: heads inside the CTA, double-buffered bulk-staged codebooks, 8 rows per warp, one CTA per SM
+      const size_t bsmem = (2 * (size_t)dim * kp + kp) * sizeof(float) + 2 * sizeof(uint64_t);
+      const int quantum = VQ_WARPS * 8;
+      int rows_per_cta = std::max(quantum, (int)ceil_div(n_rows, sms));
+      rows_per_cta = ceil_div(rows_per_cta, quantum) * quantum;
+      const int grid = ceil_div(n_rows, rows_per_cta);
+#define LAUNCH_VQB(V, Q)                                                                                       \
+  do {                                                                                                        \
+    cudaFuncSetAttribute(vq_search_bulk_kernel<64, V, Q, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                         (int)bsmem);                                                                         \
+    vq_search_bulk_kernel<64, V, Q, 8><<<grid, VQ_WARPS * 32, bsmem, st>>>(z, ld_z, embed, quant_raw, quant_st, \
+                                                                           diff, idx, n_rows, n_heads,        \
+                                                                           rows_per_cta);                     \
+  } while (0)
+      if (vec == 2) LAUNCH_VQB(2, 1);
+      else if (kq == 1) LAUNCH_VQB(4, 1);
+      else LAUNCH_VQB(4, 2);
+#undef LAUNCH_VQB
+      MSMC_CHECK_LAUNCH();
+      return MSMC_OK;
+    }
+    // 8 rows per warp halve the shared-memory traffic per FMA (at 4 rows the LDS.128 stream takes as long as the
+    // FMAs); 4 rows keep enough CTAs in flight when there are fewer than ~2k rows
+    const bool r8 = n_rows >= 2048;
+    const int warps = 8, rpw = r8 ? 8 : 4, grp = r8 ? 1 : 2;
     const int rpp = warps * rpw;
     const size_t csmem = ((size_t)dim * kp + kp + 2 * (size_t)grp * rpp * dim) * sizeof(float) + sizeof(uint64_t);
     // one wave of clusters: 2 CTAs per SM (<= 97 KB of shared memory, <= 128 registers x 256 threads each)
@@ -549,9 +729,9 @@ extern "C" int msmc_vq_search(const float* z, int64_t ld_z, const float* embed, 
                            diff, idx, (int)n_rows, rows_per_cta) != cudaSuccess)                              \
       return MSMC_ERR_LAUNCH;                                                                                 \
   } while (0)
-    if (vec == 2) { if (big) LAUNCH_VQC(2, 1, 8, 8, 1); else LAUNCH_VQC(2, 1, 4, 8, 2); }
-    else if (kq == 1) { if (big) LAUNCH_VQC(4, 1, 8, 8, 1); else LAUNCH_VQC(4, 1, 4, 8, 2); }
-    else { if (big) LAUNCH_VQC(4, 2, 8, 8, 1); else LAUNCH_VQC(4, 2, 4, 8, 2); }
+    if (vec == 2) { if (r8) LAUNCH_VQC(2, 1, 8, 8, 1); else LAUNCH_VQC(2, 1, 4, 8, 2); }
+    else if (kq == 1) { if (r8) LAUNCH_VQC(4, 1, 8, 8, 1); else LAUNCH_VQC(4, 1, 4, 8, 2); }
+    else { if (r8) LAUNCH_VQC(4, 2, 8, 8, 1); else LAUNCH_VQC(4, 2, 4, 8, 2); }
 #undef LAUNCH_VQC
     MSMC_CHECK_LAUNCH();
     return MSMC_OK;
