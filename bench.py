@@ -57,6 +57,21 @@ def synth_batch(B, seed, device="cpu", pin=False):
     return batch
 
 
+def family_traffic(entry):
+    """DRAM bytes per launch of one C-ABI entry point's kernels, from the newest committed ncu capture of this same
+    step (profiles/r*_family_traffic.json, written by profiles/family_traffic.py); None when there is none"""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_family_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        with open(files[-1]) as f:
+            d = json.load(f)["families"].get(entry)
+        return (d["dram_bytes_per_launch"] if d else None), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return None, None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -379,10 +394,14 @@ def run_b200(args, rank, world, local_rank):
                         "share": round(v["ms"] / tot_ms, 3)} for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
         top = max(fam.items(), key=lambda kv: kv[1]["ms"])
         tname, t = top
+        traffic, traffic_src = family_traffic(tname)
         if t["flops"] > 0:
             ach = t["flops"] / (t["ms"] * 1e-3) / 1e12
             roof = {"kernel": tname, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"],
-                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": traffic,
+                    "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                    "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": t["bytes"] / max(1, t["calls"]),
                     "peak_source": pk["source"] + "; the kernel computes fp32-accurate results as 3xTF32 (three "
                                    "tcgen05 kind::tf32 MMAs per K-step), its algorithmic fp32 flops are measured "
                                    "against the dense bf16 tensor peak",
@@ -392,15 +411,16 @@ def run_b200(args, rank, world, local_rank):
         else:
             ach = t["bytes"] / (t["ms"] * 1e-3) / 1e9 if t["bytes"] else 0.0
             roof = {"kernel": tname, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"]}
+                    "frac": ach / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": pk["source"]}
         vq = vq_bandwidth(device, pk)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, threads, ncpu = time_cpu_steps(cfg, 2, 1, CPU_SAMPLE_B)
+        v, dt, threads, ncpu = time_cpu_steps(cfg, 10, 2, CPU_SAMPLE_B)
         cpu = {"value": v, "unit": "mel-frames/s", "cores": threads, "kind": "port",
-               "sample": "oracle port of the same full GAN step on a B=%d slice of the batch, 2 timed steps after 1 "
-                         "warm-up (%.1f s/step); %d torch threads = fastest of a sweep up to the host's %d logical "
+               "sample": "oracle port of the same full GAN step on a B=%d slice of the batch, 10 timed steps after 2 "
+                         "warm-ups (%.1f s/step); %d torch threads = fastest of a sweep up to the host's %d logical "
                          "CPUs" % (CPU_SAMPLE_B, dt, threads, ncpu)}
     if rank == 0:
         line = json.dumps({
