@@ -281,7 +281,9 @@ def vq_bandwidth(device, pk):
     out["at_config"] = {"rows": [3840, 960], "us": [ms1 * 1e3, ms2 * 1e3],
                         "gbs": n_bytes / ((ms1 + ms2) * 1e-3) / 1e9,
                         "frac_of_hbm_peak": n_bytes / ((ms1 + ms2) * 1e-3) / 1e9 / pk["hbm_gbs"],
-                        "note": "latency-bound: %.1f MB of traffic is < 3 us at HBM peak" % (n_bytes / 1e6)}
+                        "note": "fixed-cost / fp32-FMA bound, not HBM bound: %.1f MB of traffic is < 3 us at the HBM "
+                                "peak, the %d M codeword FMAs alone are >= 7 us of CUDA-core time (DESIGN.md section 3)"
+                                % (n_bytes / 1e6, (3840 + 960) * heads * dim * K // 1000000)}
     sweep = {}
     for p in (12, 14, 16, 18, 20, 22):
         g, ms = run(1 << p, 10 if p < 20 else 3)
