@@ -373,6 +373,71 @@ __global__ void __launch_bounds__(DS_THREADS) conv_direct_small_kernel(const Con
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One source channel, many destination channels: the data gradients of the discriminators' score convolutions
+// (C -> 1 forward, hence 1 -> C in conv-transpose form) and of the generator's conv_post.  The contraction is an outer
+// product per tap (K = taps x 1), so a GEMM tile is all padding: here one thread owns 4 destination channels of one
+// position, the weight [tap][Cd] sits in shared memory, the few source scalars come through L1 (the Cd/4 threads of a
+// position read the same addresses) and the store is one coalesced 16-byte write per thread -- the kernel is bound
+// by writing dst.  src_coord() gives forward and conv-transpose forms.
+// ------------------------------------------------------------------------------------------------
+constexpr int C1_THREADS = 256;
+constexpr int C1_MAX_W = 8192;   // taps x Cd weight floats in shared memory
+
+__global__ void __launch_bounds__(C1_THREADS) conv_c1_kernel(const ConvArgs a) {
+  const msmc_conv_geom& g = a.g;
+  __shared__ __align__(16) float s_w[C1_MAX_W];
+  const int T = g.KH * g.KW;
+  for (int e = threadIdx.x; e < T * g.Cd; e += C1_THREADS) {
+    const int n = e % g.Cd, t = e / g.Cd;
+    const int kh = t / g.KW, kw = t - kh * g.KW;
+    s_w[e] = __ldg(a.w + kh * g.ws_kh + kw * g.ws_kw + (int64_t)n * g.ws_cd);
+  }
+  __syncthreads();
+  const int cd4 = g.Cd >> 2;                       // <= 256
+  const int P = C1_THREADS / cd4;                  // positions per CTA pass
+  const int cg = threadIdx.x % cd4, pl = threadIdx.x / cd4;
+  if (pl >= P) return;
+  const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
+  const unsigned hw = (unsigned)(g.Hd * g.Wd);
+  const bool need_aux = xf_needs_aux(g.src_xf), dneed_aux = xf_needs_aux(g.dst_xf);
+  const float4* w4 = reinterpret_cast<const float4*>(s_w);
+  for (int64_t m = (int64_t)blockIdx.x * P + pl; m < M; m += (int64_t)gridDim.x * P) {
+    const int b = (int)((unsigned)m / hw);
+    const int rem = (int)((unsigned)m - (unsigned)b * hw);
+    const int hd = (int)((unsigned)rem / (unsigned)g.Wd), wd = rem - hd * g.Wd;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kh = 0; kh < g.KH; ++kh)
+      for (int kw = 0; kw < g.KW; ++kw) {
+        int hs, ws;
+        if (!src_coord(g, hd, wd, kh, kw, hs, ws)) continue;
+        const int64_t off = ((int64_t)b * g.Hs + hs) * g.Ws + ws;
+        float v = __ldg(a.src + off * g.ld_src);
+        if (g.src_xf != MSMC_XF_NONE)
+          v = apply_xf(g.src_xf, g.src_slope, v, need_aux ? __ldg(a.src_aux + off * g.ld_saux) : 0.f);
+        const float4 w = w4[(kh * g.KW + kw) * cd4 + cg];
+        acc.x = fmaf(v, w.x, acc.x); acc.y = fmaf(v, w.y, acc.y);
+        acc.z = fmaf(v, w.z, acc.z); acc.w = fmaf(v, w.w, acc.w);
+      }
+    const int n = cg * 4;
+    if (a.bias) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+      acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
+    }
+    if (g.dst_xf != MSMC_XF_NONE) {
+      float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dneed_aux) av = __ldg(reinterpret_cast<const float4*>(a.dst_aux + m * g.ld_daux + n));
+      acc.x = apply_xf(g.dst_xf, g.dst_slope, acc.x, av.x); acc.y = apply_xf(g.dst_xf, g.dst_slope, acc.y, av.y);
+      acc.z = apply_xf(g.dst_xf, g.dst_slope, acc.z, av.z); acc.w = apply_xf(g.dst_xf, g.dst_slope, acc.w, av.w);
+    }
+    if (a.residual) {
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(a.residual + m * g.ld_res + n));
+      acc.x += rv.x; acc.y += rv.y; acc.z += rv.z; acc.w += rv.w;
+    }
+    *reinterpret_cast<float4*>(a.dst + m * g.ld_dst + n) = acc;
+  }
+}
+
 bool direct_small_eligible(const msmc_conv_geom& g) {
   if (g.Cs > 16 || g.Cd > 16) return false;
   const int cdp = g.Cd <= 4 ? 4 : (g.Cd <= 8 ? 8 : 16);
@@ -889,6 +954,17 @@ extern "C" int msmc_conv_forward(const msmc_conv_geom* gp, const float* src, con
               (!xf_needs_aux(g.src_xf) || ((g.ld_saux % 4 == 0) && aligned16(src_aux)));
   a.b_kmajor = (g.ws_cd != 1 && g.ws_cs == 1);
   cudaStream_t st = (cudaStream_t)stream;
+  if (g.Cs == 1 && g.Cd >= 32 && g.Cd <= 1024 && (g.Cd & 3) == 0 && (int64_t)g.KH * g.KW * g.Cd <= C1_MAX_W &&
+      (g.ld_dst & 3) == 0 && aligned16(dst) && (!bias || aligned16(bias)) &&
+      (!residual || ((g.ld_res & 3) == 0 && aligned16(residual))) &&
+      (!xf_needs_aux(g.dst_xf) || ((g.ld_daux & 3) == 0 && aligned16(dst_aux)))) {
+    const int64_t Mall = (int64_t)g.B * g.Hd * g.Wd;
+    const int P = C1_THREADS / (g.Cd >> 2);
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(Mall, P), (int64_t)num_sms() * 8);
+    conv_c1_kernel<<<blocks, C1_THREADS, 0, st>>>(a);
+    MSMC_CHECK_LAUNCH();
+    return MSMC_OK;
+  }
   if (direct_small_eligible(g)) {
     a.vec_src = (g.Cs % 4 == 0) && (g.ld_src % 4 == 0) && aligned16(src) &&
                 (!xf_needs_aux(g.src_xf) || ((g.ld_saux % 4 == 0) && aligned16(src_aux)));

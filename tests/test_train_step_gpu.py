@@ -55,3 +55,33 @@ def test_two_train_steps_vs_oracle(reference_schedule):
     for k, v in oracle.sd_ae.items():
         if k.split(".")[-1] == "cluster_size":
             assert torch.allclose(sd_gpu[k].cpu(), v.detach(), rtol=1e-2, atol=1e-3), k
+
+
+def test_cuda_graph_replay_matches_eager_steps():
+    """bench.py times the step as a CUDA-graph replay (3 eager warm-ups, capture, replay): the captured step --
+    forked branch / weight-gradient / prefetch streams, graph-private pointer tables of the multi-tensor kernels,
+    device-side step counter -- must produce the same losses and the same parameters as the eager step."""
+    import bench
+    cfg = bench.load_cfg()
+    cfg["autoencoder"]["quantizer_config"]["embedding_sizes"] = 64
+    dev = torch.device("cuda:0")
+    B = 2
+    batch = {k: v.to(dev) for k, v in bench.synth_batch(B, 11).items()}
+    win = [(100, 140), (20, 60)]
+    logs, params = [], []
+    for use_graph in (False, True):
+        trainer = bench.build_gpu_trainer(cfg, dev, False, 0, 1, use_graph=use_graph)
+        _no_dropout(trainer.model)
+        out = []
+        for step in range(6):            # graph mode: steps 0-2 eager warm-up, step 3 capture + replay, 4-5 replays
+            log = trainer.train_step(batch, iteration=10 + step, frame_windows=win)["loss"]
+            out.append({k: float(v) for k, v in log.items() if torch.is_tensor(v)})
+        torch.cuda.synchronize()
+        logs.append(out)
+        params.append([p.detach().clone() for p in trainer.model.parameters()])
+    for step, (a, b) in enumerate(zip(*logs)):
+        for k in ("vq_loss", "frame_loss", "stft_loss", "d_loss", "fm_loss", "adv_loss", "g_loss"):
+            assert abs(a[k] - b[k]) <= 1e-4 * max(abs(a[k]), 1e-3), "step %d %s: eager %.7f graph %.7f" % (
+                step, k, a[k], b[k])
+    worst = max(float((x - y).abs().max()) for x, y in zip(*params))
+    assert worst <= 1e-4, "parameters after 6 steps differ by %.3e" % worst
