@@ -1459,14 +1459,15 @@ __global__ void weight_image_kernel(const float* __restrict__ w, float* __restri
 // N tile.  Measured on B200 (profiles/r01_sweep_bn.txt): the tensor pipe retires a 128 x N x 8 TF32 MMA in roughly
 // the same time for N = 32 and N = 128, so the widest tile wins almost everywhere -- even when it leaves fewer CTAs
 // than SMs (FFN-2 at M = 3840: 60 CTAs of N = 128 take 61 us, 240 CTAs of N = 32 take 82 us).  Only when the grid
-// would shrink below ~32 CTAs does the narrower tile's extra parallelism pay (256 -> 256 linear at M = 960).
+// would shrink below ~16 CTAs does the narrower tile's extra parallelism pay (whole step: 41.45 ms at a threshold
+// of 32, 41.09 ms at 16, 42.08 ms at 64).
 int umma_pick_bn(int cd, int64_t rows) {
   // bring-up / sweep override (profiles/sweep_bn.py): MSMC_FORCE_BN=32|64|128, read per call
   if (const char* e = getenv("MSMC_FORCE_BN")) {
     const int f = atoi(e);
     if ((f == 32 || f == 64 || f == 128) && !(f > 32 && cd <= f / 2)) return f;
   }
-  static const int min_ctas = [] { const char* e = getenv("MSMC_BN_MIN_CTAS"); return e ? atoi(e) : 32; }();
+  static const int min_ctas = [] { const char* e = getenv("MSMC_BN_MIN_CTAS"); return e ? atoi(e) : 16; }();
   const int64_t mt = ceil_div64(rows, UM_BM);
   const int cands[3] = {128, 64, 32};
   for (int i = 0; i < 3; ++i) {
