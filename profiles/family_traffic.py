@@ -15,7 +15,7 @@ FAMILY = [
     (r"conv_wgrad_umma_kernel|conv_wgrad_reuse_kernel", "msmc_conv_wgrad_umma"),
     (r"conv_umma_reuse_kernel", "msmc_conv_forward_umma_reuse"),
     (r"conv_umma_kernel", "msmc_conv_forward_umma"),
-    (r"conv_gemm_kernel|conv_direct_small_kernel", "msmc_conv_forward"),
+    (r"conv_gemm_kernel|conv_direct_small_kernel|conv_c1_kernel", "msmc_conv_forward"),
     (r"conv_wgrad_kernel|conv_wgrad_small_kernel", "msmc_conv_wgrad"),
     (r"wgrad_reduce_kernel", "wgrad_reduce (second pass of both weight-gradient entry points)"),
     (r"weight_image_kernel", "msmc_weight_image"),
