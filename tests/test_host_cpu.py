@@ -168,3 +168,40 @@ def test_gradient_allreduce_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_tile_policy_and_workspace_queries_run_without_a_gpu():
+    """host-side planning entry points of the C-ABI are pure functions of the geometry (no device work): the N-tile
+    policy (widest tile unless the grid would fall below 16 CTAs, never pad N by more than 2x) and
+    the operand-image / workspace sizes the Python side allocates from"""
+    from msmctts._b200 import lib as L
+    lib = L.load()
+    assert lib.msmc_umma_tile_n(1024, 3840) == 128      # FFN-1
+    assert lib.msmc_umma_tile_n(256, 3840) == 128       # FFN-2: 60 CTAs of N = 128 beat 240 of N = 32
+    assert lib.msmc_umma_tile_n(256, 960) == 128        # 8 x 2 = 16 CTAs: still the wide tile
+    assert lib.msmc_umma_tile_n(256, 256) == 32         # 2 x 2 = 4 CTAs -> narrow tiles for parallelism
+    assert lib.msmc_umma_tile_n(32, 192000) == 32       # never pad 32 channels to 64
+    assert lib.msmc_umma_tile_n(64, 96000) == 64
+    assert lib.msmc_umma_tile_n(1, 12000) == 32
+    # image size: T taps x (K/32) chunks x n-tiles x BN rows x 32 floats x (hi, lo planes)
+    assert lib.msmc_weight_image_elems(3, 256, 1024, 0, 1, 128) == 3 * 8 * 8 * 128 * 32 * 2
+    assert lib.msmc_weight_image_elems(3, 100, 64, 0, 1, 64) == -1        # K not a multiple of 32
+    assert lib.msmc_adam_chunk_elems() > 0 and lib.msmc_l1_chunk_elems() > 0
+
+
+def test_dense_permutation_of_feature_map_views():
+    """the fused feature-matching loss runs on the underlying channels-last buffers: `_dense_perm` must find the
+    permutation that makes a permuted view contiguous, and its inverse must restore shape and strides"""
+    import torch
+    from msmctts._b200.functional import _dense_perm
+    base = torch.arange(2 * 5 * 7 * 3, dtype=torch.float32).reshape(2, 5, 7, 3)      # (B, H, W, C)
+    for dims in [(0, 3, 1, 2), (0, 3, 2, 1), (0, 1, 2, 3), (3, 0, 2, 1)]:
+        view = base.permute(*dims)
+        perm = _dense_perm(view)
+        assert perm is not None and view.permute(perm).is_contiguous()
+        inv = [0] * len(perm)
+        for i, d in enumerate(perm):
+            inv[d] = i
+        back = view.permute(perm).permute(inv)
+        assert back.shape == view.shape and back.stride() == view.stride()
+    assert _dense_perm(base[:, :, ::2]) is None        # strided slice: not dense under any permutation
