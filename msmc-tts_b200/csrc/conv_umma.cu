@@ -28,7 +28,6 @@ namespace {
 
 constexpr int UM_BM = 128;
 constexpr int UM_BK = 32;       // tf32 per stage row (128 B)
-constexpr int UM_THREADS = 160;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -68,31 +67,11 @@ __device__ __forceinline__ void publish_and_arrive_warp(uint64_t* bar) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 = 1 | [32,46) SBO>>4 = 64 (8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = 2
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)64 << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      :
-      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // The MMA-issuing thread is instruction-bound at N <= 64 (a 128 x 64 x 8 TF32 MMA occupies the tensor pipe for only
 // 32 cycles), so descriptors are built from a per-stage low word plus compile-time offsets: the high word
 // (SBO, version, layout) is an immediate, the low word (start >> 4 | LBO << 16) advances by plain 32-bit adds.
@@ -587,7 +566,7 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
   const int KC = g.Cs / UM_BK;
   const int T = a.n_taps;
   const int r_in = UM_BM + (T - 1) * a.tap_stride;      // rows staged per chunk (<= RU_ROWS)
-  constexpr int MMA_WARP = RU_PRODUCERS / 32, LOAD_WARP = MMA_WARP + 1;
+  constexpr int MMA_WARP = RU_PRODUCERS / 32;   // warp MMA_WARP + 1 streams the weight tiles
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&fa[i], RU_PRODUCERS / 32); mbar_init(&ea[i], 1); }
@@ -817,18 +796,9 @@ struct UmmaWgradArgs {
                            //                            2 = producers load and store but the MMA warp issues nothing
 };
 
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
-  // MN-major TF32 operands only exist in the SWIZZLE_128B_BASE32B layout (layout type 1, cute
-  // Layout_MN_SW128_32B_Atom: 128-byte rows of 32 MN elements, 4 K-rows per atom, 32-byte chunks XORed with
-  // row & 3).  LBO = 4096 B between 32-element MN blocks, SBO = 512 B between 4-row K groups.
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(4096 >> 4) << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)1 << 61;
-  return d;
-}
+// MN-major TF32 operands only exist in the SWIZZLE_128B_BASE32B layout (layout type 1, cute
+// Layout_MN_SW128_32B_Atom: 128-byte rows of 32 MN elements, 4 K-rows per atom, 32-byte chunks XORed with
+// row & 3).  LBO = 4096 B between 32-element MN blocks, SBO = 512 B between 4-row K groups (desc_lo_mn / DESC_HI_MN).
 // byte offset of 16-byte chunk `c16` of K-row `p` inside one 32-channel block of an MN-major operand tile
 __device__ __forceinline__ uint32_t mn_off(int p, int c16) {
   return (uint32_t)p * 128u + (uint32_t)(((((c16 >> 1) ^ (p & 3)) << 1) | (c16 & 1)) << 4);
