@@ -293,6 +293,30 @@ def vq_bandwidth(device, pk):
     return out
 
 
+def vq_cpu_port(threads):
+    """the reference's MultiHeadQuantize search (oracle port of vqgantts/modules.py:24-33,137-151, eval mode) on the
+    host cores at the training shape: the CPU figure that belongs next to `vq_argmin.at_config`"""
+    from oracle import ref_modules as O
+    torch.set_num_threads(threads)
+    heads, dim, K = 4, 64, K_CODEWORDS
+    g = torch.Generator().manual_seed(5)
+    sd = {"q.quantizers.%d.embed" % h: torch.randn(dim, K, generator=g) for h in range(heads)}
+    us, n_bytes = [], 0
+    for t in (T_FRAMES, T_FRAMES // 4):
+        x = torch.randn(B_PER_GPU, t, heads * dim, generator=g)
+        with torch.no_grad():
+            O.multihead_quantize(sd, "q.", x, heads)
+            reps = 5
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                O.multihead_quantize(sd, "q.", x, heads)
+            us.append((time.perf_counter() - t0) / reps * 1e6)
+        n = B_PER_GPU * t
+        n_bytes += n * (heads * dim * 4 * 3 + dim * 4 + heads * 8) + heads * dim * K * 4
+    return {"rows": [B_PER_GPU * T_FRAMES, B_PER_GPU * T_FRAMES // 4], "us": us, "cores": threads, "kind": "port",
+            "gbs": n_bytes / (sum(us) * 1e-6) / 1e9}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
     from msmctts._b200 import lib as L
@@ -424,6 +448,8 @@ def run_b200(args, rank, world, local_rank):
                "sample": "oracle port of the same full GAN step on a B=%d slice of the batch, 10 timed steps after 2 "
                          "warm-ups (%.1f s/step); %d torch threads = fastest of a sweep up to the host's %d logical "
                          "CPUs" % (CPU_SAMPLE_B, dt, threads, ncpu)}
+        if vq is not None:
+            vq["cpu_port_at_config"] = vq_cpu_port(threads)
     if rank == 0:
         line = json.dumps({
             "metric": "mel-frames/sec MSMC-VQ-GAN train step", "value": value, "unit": "mel-frames/s",
