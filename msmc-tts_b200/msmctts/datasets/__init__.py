@@ -9,8 +9,14 @@ from torch.utils.data.distributed import DistributedSampler
 class SyntheticMelDataset(Dataset):
     """mel = clamp(1.5 N(0,1), -4, 4) (B,T,80); wav = clamp(0.3 N(0,1), -1, 1) (300 T, 1); lengths all T"""
 
-    def __init__(self, n_items=1024, n_frames=240, n_mels=80, frameshift=300, seed=1234, **_):
-        self.n_items, self.n_frames, self.n_mels, self.frameshift, self.seed = n_items, n_frames, n_mels, frameshift, seed
+    def __init__(self, n_items=1024, n_frames=240, n_mels=80, frameshift=300, seed=1234, feature=None, **_):
+        # the reference yaml gives one frameshift per feature (dataset.feature / dataset.frameshift lists,
+        # examples/csmsc/configs/msmc_vq_gan.yaml): the mel entry is the hop
+        if isinstance(frameshift, (list, tuple)):
+            names = list(feature) if feature is not None else []
+            frameshift = frameshift[names.index("mel")] if "mel" in names else max(frameshift)
+        self.n_items, self.n_frames, self.n_mels, self.seed = n_items, n_frames, n_mels, seed
+        self.frameshift = int(frameshift)
 
     def __len__(self):
         return self.n_items
