@@ -60,6 +60,28 @@ class QuantizerLoss(nn.Module):
         return loss
 
 
+_LSGAN_WEIGHTS = {}
+
+
+def lsgan_loss(scores, target):
+    """sum_i F.mse_loss(s_i, full_like(s_i, target)) over a list of score tensors (reference :165-168, :184-185) in
+    one pass: the scores are concatenated and each element carries the weight 1 / numel(s_i).  ~7 tiny launches per
+    score (fill, sub, pow, mean and their backward) become ~10 per LOSS; they sit on the serial stretch between the
+    discriminator's forward and backward."""
+    scores = list(scores)
+    key = (tuple(int(s.numel()) for s in scores), scores[0].device)
+    w = _LSGAN_WEIGHTS.get(key)
+    if w is None:
+        if scores[0].is_cuda and torch.cuda.is_current_stream_capturing():
+            # never cache memory that belongs to a CUDA graph's private pool: per-score form for this one call
+            return sum(F.mse_loss(s, torch.full_like(s, float(target))) for s in scores)
+        w = torch.cat([torch.full((n,), 1.0 / n, dtype=torch.float32, device=key[1]) for n in key[0]])
+        _LSGAN_WEIGHTS[key] = w
+    flat = torch.cat([s.reshape(-1) for s in scores])
+    d = flat - float(target)
+    return (d * d * w).sum()
+
+
 @contextlib.contextmanager
 def _frozen(module):
     """parameters of `module` do not require grad inside the block (custom autograd Functions decide at forward time
@@ -221,8 +243,11 @@ class VQGANTrainer(BaseTrainer):
                 nb = predict.shape[0]
                 both, _ = disc(torch.cat([predict.detach(), target], dim=0))
                 fake_scores, real_scores = [s[:nb] for s in both], [s[nb:] for s in both]
-            d_real = sum(F.mse_loss(s, torch.ones_like(s)) for s in real_scores)
-            d_fake = sum(F.mse_loss(s, torch.zeros_like(s)) for s in fake_scores)
+            if self.reference_schedule:
+                d_real = sum(F.mse_loss(s, torch.ones_like(s)) for s in real_scores)
+                d_fake = sum(F.mse_loss(s, torch.zeros_like(s)) for s in fake_scores)
+            else:
+                d_real, d_fake = lsgan_loss(real_scores, 1.0), lsgan_loss(fake_scores, 0.0)
             d_loss = d_real + d_fake
             losses.update(d_loss_real=d_real, d_loss_fake=d_fake, d_loss=d_loss)
             self.optimizer.zero_grad(["discriminator"])
@@ -239,7 +264,8 @@ class VQGANTrainer(BaseTrainer):
                     fake_scores, fake_feats = disc(predict)
                     with torch.no_grad():
                         _, real_feats = disc(target)
-            adv = sum(F.mse_loss(s, torch.ones_like(s)) for s in fake_scores)
+            adv = sum(F.mse_loss(s, torch.ones_like(s)) for s in fake_scores) if self.reference_schedule \
+                else lsgan_loss(fake_scores, 1.0)
             if self.reference_schedule or not predict.is_cuda:
                 fm = sum(F.l1_loss(a, b) for fa, fb in zip(fake_feats, real_feats) for a, b in zip(fa, fb))
             else:

@@ -267,3 +267,27 @@ def test_train_cli_fails_loudly_without_a_gpu(tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode != 0
     assert "MsmcError" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def test_batched_lsgan_loss_equals_sum_of_mse_terms():
+    """trainer.lsgan_loss == sum_i F.mse_loss(s_i, target) (reference trainers/msmctts_trainer.py:165-168,184-185),
+    values and gradients, on score tensors of different sizes and on slices of a shared buffer (the discriminator
+    step scores cat(fake, real) and slices the halves).  Tolerance 1e-6 relative: summation order only."""
+    import torch
+    import torch.nn.functional as F
+    from msmctts.trainers.msmctts_trainer import lsgan_loss
+    torch.manual_seed(0)
+    sizes = [(4, 1, 25, 13), (4, 120), (4, 1, 7), (4, 333), (4, 1, 2000, 2)]
+    both = [torch.randn((8,) + s[1:], requires_grad=True) for s in sizes]
+    ref_in = [b.detach().clone().requires_grad_(True) for b in both]
+    for target in (1.0, 0.0):
+        mine = lsgan_loss([b[:4] for b in both], target) + 0.5 * lsgan_loss([b[4:] for b in both], 1.0 - target)
+        ref = sum(F.mse_loss(r[:4], torch.full_like(r[:4], target)) for r in ref_in) + \
+            0.5 * sum(F.mse_loss(r[4:], torch.full_like(r[4:], 1.0 - target)) for r in ref_in)
+        assert abs(float(mine) - float(ref)) <= 1e-6 * abs(float(ref))
+        for t in both + ref_in:
+            t.grad = None
+        mine.backward()
+        ref.backward()
+        for a, b in zip(both, ref_in):
+            assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-9)
