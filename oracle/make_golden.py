@@ -247,6 +247,61 @@ def gen_predictor():
                               duration=out["duration"].detach(), loss=loss.detach(), grads=grads))
 
 
+def gen_train_step():
+    """Two consecutive `VQGANTrainer.train_step` calls of the UNMODIFIED reference trainer
+    (trainers/msmctts_trainer.py:115-209: losses, D step, G step, clip, AdamW through the reference's own
+    build_optimizer) on CPU, small config.  Pins oracle/train_step.py -- the port that the whole-step GPU parity test
+    and bench.py's CPU arm run.  The window draw (random.randrange, :211-219) is made reproducible by seeding
+    Python's RNG before each step; the fixture records the windows it produced."""
+    import random
+    V = R.ref("msmctts.networks.vqgantts.msmc_vqgan")
+    D = R.ref("msmctts.networks.hifigan.discriminator")
+    T = R.ref("msmctts.trainers.msmctts_trainer")
+    O = R.ref("msmctts.trainers.optimizers")
+    torch.manual_seed(21)
+    cfg = json.loads(json.dumps(SMALL_AE))
+    cfg["decoder_config"].update(upsample_rates=[10, 2], upsample_kernel_sizes=[20, 4])    # 20 samples per frame
+    ae = V.MSMCVQGAN(cfg["in_dim"], cfg["n_model_size"], cfgitem(cfg["encoder_config"]),
+                     cfgitem(cfg["quantizer_config"]), cfgitem(cfg["frame_decoder_config"]),
+                     cfgitem(cfg["decoder_config"]), cfg["pred_mel"])
+    for k, p in ae.named_parameters():
+        if k.startswith("decoder."):
+            p.data.mul_(3.0).add_(0.02 * torch.randn_like(p))
+    for pr in ae.quantizer.predictor:   # harness tweak: ResStack's hard-wired Dropout(0.1) -> 0
+        pr.enc.drop.p = 0.0
+    disc = D.Discriminator(cfgitem(SMALL_D["mrd_config"]), cfgitem(SMALL_D["mpd_config"]))
+    model = torch.nn.Module()
+    model.autoencoder, model.discriminator = ae, disc
+    model.train()
+    tcfg = dict(warmup_steps=0, lambda_frame=450, grad_clip_thresh=1.0, sample_lengths=1200, lambda_vq=1,
+                lambda_pr=0.1, lambda_fm=2, lambda_stft=45)
+    ocfg = dict(_name="AdamW", learning_rate=0.0002, betas=[0.8, 0.99], eps=1e-8, weight_decay=0.0)
+    config = cfgitem(dict(dataset=dict(samplerate=24000, feature=["mel", "wav"], frameshift=[20, 1]),
+                          optimizer=dict(_default=ocfg)))
+    trainer = T.VQGANTrainer(config, model, num_gpus=0, rank=0, **tcfg)
+    trainer.optimizer = O.build_optimizer(model, config.optimizer)
+    B, frames = 2, 80
+    mel = (1.5 * torch.randn(B, frames, cfg["in_dim"])).clamp(-4, 4)
+    wav = (0.3 * torch.randn(B, frames * 20, 1)).clamp(-1, 1)
+    length = torch.tensor([80, 71])
+    batch = dict(mel=mel, mel_length=length, wav=wav, wav_length=length * 20)
+    sd_ae0, sd_d0 = clone_sd(ae), clone_sd(disc)
+    steps = []
+    for it in (1, 2):
+        random.seed(100 + it)
+        windows = [(s, s + 60) for s in (random.randrange(max(1, int(n) - 60)) for n in length)]
+        random.seed(100 + it)
+        log = trainer.train_step(batch, iteration=it)["loss"]
+        steps.append(dict(windows=windows, losses={k: float(v) for k, v in log.items()}))
+    # after two steps: every 4th tensor plus all codebook buffers (keeps the fixture small)
+    keep = lambda sd: {k: v for i, (k, v) in enumerate(sd.items())
+                       if i % 4 == 0 or k.split(".")[-1] in ("embed", "embed_avg", "cluster_size")}
+    save("train_step.pt", dict(cfg=dict(autoencoder=cfg, discriminator=SMALL_D), trainer=dict(tcfg, frameshift=20,
+                               sample_rate=24000), optimizer=ocfg, sd_ae=sd_ae0, sd_d=sd_d0, mel=mel, wav=wav,
+                               length=length, steps=steps, sd_ae_after=keep(clone_sd(ae)),
+                               sd_d_after=keep(clone_sd(disc))))
+
+
 def gen_keys():
     """state_dict names + shapes of the full CSMSC models (examples/csmsc/configs/msmc_vq_gan.yaml)."""
     C = R.ref("msmctts.utils.config")
@@ -287,4 +342,5 @@ if __name__ == "__main__":
     gen_melloss()
     gen_autoencoder()
     gen_predictor()
+    gen_train_step()
     gen_keys()

@@ -35,7 +35,7 @@ class OracleTrainer(object):
         t = self.tcfg
         losses, g_loss, predict, target, _ = O.generator_losses(
             self.sd_ae, self.sd_d, self.cfg, mel, mel_length, wav, windows,
-            dict(t, frameshift=300, sample_rate=24000), training=True, use_dropout=self.use_dropout)
+            dict(dict(frameshift=300, sample_rate=24000), **t), training=True, use_dropout=self.use_dropout)
         self.opt_d.zero_grad(set_to_none=True)
         losses["d_loss"].backward()
         self.opt_d.step()
