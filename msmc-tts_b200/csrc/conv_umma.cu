@@ -804,28 +804,8 @@ __device__ __forceinline__ uint32_t mn_off(int p, int c16) {
   return (uint32_t)p * 128u + (uint32_t)(((((c16 >> 1) ^ (p & 3)) << 1) | (c16 & 1)) << 4);
 }
 
-// 4x4 transpose across the 4 lanes that share a 16-byte chunk index (lane bits 3,4 = position sub-index):
-// in : lane p holds 4 channels of position p      out: lane p holds channel p at 4 consecutive positions
-__device__ __forceinline__ float4 transpose4_lanes(float4 x, int psub) {
-  {  // exchange the off-diagonal 2x2 blocks (partner: psub ^ 2)
-    const bool lo = psub < 2;
-    const float s0 = lo ? x.z : x.x, s1 = lo ? x.w : x.y;
-    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
-    if (lo) { x.z = r0; x.w = r1; } else { x.x = r0; x.y = r1; }
-  }
-  {  // transpose inside each 2x2 block (partner: psub ^ 1)
-    const bool ev = (psub & 1) == 0;
-    const float s0 = ev ? x.y : x.x, s1 = ev ? x.w : x.z;
-    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 8), r1 = __shfl_xor_sync(0xffffffffu, s1, 8);
-    if (ev) { x.y = r0; x.w = r1; } else { x.x = r0; x.z = r1; }
-  }
-  return x;
-}
-
-// KMAJOR = true: the producers transpose both operands in registers (warp shuffles) and store ordinary K-major
-// SWIZZLE_128B tiles (rows = channels, 128 bytes = 32 positions), so the MMAs are the same K-major instructions as
-// the forward kernel; KMAJOR = false: MN-major SWIZZLE_128B_BASE32B operands straight from the row layout.
-template <int BN, bool SPLIT, int STAGES, int XFC, bool KMAJOR>
+// (A K-major variant -- producers transposing both operands with warp shuffles -- was measured slower and removed.)
+template <int BN, bool SPLIT, int STAGES, int XFC>
 __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_umma_kernel(const UmmaWgradArgs a) {
   const msmc_conv_geom& g = a.g;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -990,15 +970,7 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
             }
             if (do_bias) { bsum[0] += x.x; bsum[1] += x.y; bsum[2] += x.z; bsum[3] += x.w; }
           }
-          uint8_t* d;
-          if (KMAJOR) {
-            // after the transpose this lane owns channel row c = chunk*4 + psub, positions 4i .. 4i+3
-            x = transpose4_lanes(x, psub);
-            const int c = chunk * 4 + psub;
-            d = base + (uint32_t)(c >> 3) * 1024u + (uint32_t)(c & 7) * 128u + (uint32_t)((i ^ (c & 7)) << 4);
-          } else {
-            d = base + mn_off(p, chunk);
-          }
+          uint8_t* d = base + mn_off(p, chunk);
           if (SPLIT) {
             const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
             *reinterpret_cast<float4*>(d) = hi;
@@ -1057,13 +1029,13 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
     tc_fence_before();
   } else {
     // ================================= MMA issuer =================================
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (KMAJOR ? 0u : ((1u << 15) | (1u << 16))) |
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((1u << 15) | (1u << 16)) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
     if ((tid & 31) == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t a_desc0 = KMAJOR ? desc_lo_k(smem_u32(sA)) : desc_lo_mn(smem_u32(sA));
-      const uint32_t b_desc0 = KMAJOR ? desc_lo_k(smem_u32(sB)) : desc_lo_mn(smem_u32(sB));
+      const uint32_t a_desc0 = desc_lo_mn(smem_u32(sA));
+      const uint32_t b_desc0 = desc_lo_mn(smem_u32(sB));
       for (int ks = 0; ks < n_k; ++ks) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
@@ -1074,8 +1046,8 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
           for (int kg = 0; kg < 4; ++kg) {
             // one MMA = 8 positions: MN-major -> two 4-row atoms (1 KB = 64 units) per 32-channel block;
             //                        K-major  -> 32 bytes (2 units) further along every 128-byte channel row
-            constexpr uint32_t KSTEP = KMAJOR ? 2u : 64u;
-            constexpr uint32_t HI = KMAJOR ? DESC_HI_K : DESC_HI_MN;
+            constexpr uint32_t KSTEP = 64u;
+            constexpr uint32_t HI = DESC_HI_MN;
             const uint32_t a_hi = ad + kg * KSTEP, b_hi = bd + kg * KSTEP;
             const uint32_t acc = (ks > 0 || kg > 0) ? 1u : 0u;
             if (SPLIT) {
@@ -1670,7 +1642,6 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
     const char* e = getenv("MSMC_WGRAD_DRY");
     a.dry = e ? atoi(e) : 0;
   }
-  static const int kmajor = [] { const char* e = getenv("MSMC_WGRAD_KMAJOR"); return e ? atoi(e) : 0; }();
   MSMC_REQUIRE(M < ((int64_t)1 << 31));
   a.div_hw = make_fastdiv((uint32_t)(g.Hd * g.Wd));
   a.div_w = make_fastdiv((uint32_t)g.Wd);
@@ -1687,15 +1658,9 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
   do {                                                                                                          \
     const size_t smem = 1024 + (size_t)ST_ * (SPLIT_ ? 2 : 1) * (4 * 4096 + (BN_ / 32) * 4096) +                \
                         (2 * ST_ + 1) * 8 + 16;                                                                 \
-    if (kmajor) {                                                                                               \
-      cudaFuncSetAttribute(conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_, true>,                                  \
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                             \
-      conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_, true><<<grid, UMF_THREADS, smem, st>>>(a);                   \
-    } else {                                                                                                    \
-      cudaFuncSetAttribute(conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_, false>,                                 \
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                             \
-      conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_, false><<<grid, UMF_THREADS, smem, st>>>(a);                  \
-    }                                                                                                           \
+    cudaFuncSetAttribute(conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_>,                                          \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                               \
+    conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_><<<grid, UMF_THREADS, smem, st>>>(a);                           \
   } while (0)
 #define LAUNCH_WG(BN_, SPLIT_, ST_)                                        \
   do {                                                                     \
