@@ -40,17 +40,25 @@ def build(verbose=True):
     stamp = " ".join(_digest(os.path.join(CSRC, src), headers) for src in sources)
     if os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read() == stamp:
         return LIB
-    objs, rebuilt = [], False
+    objs, jobs = [], []
     for src in sources:
         path = os.path.join(CSRC, src)
         obj = os.path.join(OBJ_DIR, "%s.%s.o" % (src[:-3], _digest(path, headers)))
         if not os.path.exists(obj):
-            cmd = [NVCC] + FLAGS + ["-c", path, "-o", obj]
+            jobs.append([NVCC] + FLAGS + ["-c", path, "-o", obj + ".tmp.o"])
+        objs.append(obj)
+    rebuilt = bool(jobs)
+    if jobs:
+        # translation units compile side by side (conv_umma.cu alone takes ~2.5 min); objects appear atomically
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(cmd):
             if verbose:
                 print("[build]", " ".join(cmd), flush=True)
             subprocess.check_call(cmd)
-            rebuilt = True
-        objs.append(obj)
+            os.replace(cmd[-1], cmd[-1][:-len(".tmp.o")])
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            list(pool.map(run, jobs))
     if rebuilt or not os.path.exists(LIB):
         cmd = [NVCC, "-shared", "-cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64", "-o", LIB] + objs
         if verbose:
