@@ -1,27 +1,33 @@
+"""Container of the named sub-networks a yaml `task` block describes (interface of reference
+tasks/base_task.py:6-33: sub-networks become attributes, `forward` dispatches on the construction mode)."""
 import torch
 
 from msmctts.networks import find_modules
 
 
 class BaseTask(torch.nn.Module):
-    """named sub-networks built from the yaml `task` block (reference tasks/base_task.py:6-33)"""
+    _STEP_OF_MODE = {"train": "train_step", "infer": "infer_step", "debug": "debug_step"}
 
     def __init__(self, config, mode="train"):
         super().__init__()
         self.config, self.mode = config, mode
-        modules = config.task.network if hasattr(config.task, "network") else \
-            {k: v for k, v in config.task.items() if k[:1] != "_" and "_name" in v}
-        for name, network in find_modules(modules):
+        task = config.task
+        if hasattr(task, "network"):
+            blocks = task.network
+        else:                      # every non-directive entry that names a class is a sub-network
+            blocks = {k: v for k, v in task.items() if not k.startswith("_") and "_name" in v}
+        for name, network in find_modules(blocks):
             self.add_module(name, network)
 
     def forward(self, features):
-        return {"train": self.train_step, "infer": self.infer_step, "debug": self.debug_step}[self.mode](features)
+        return getattr(self, self._STEP_OF_MODE[self.mode])(features)
 
+    # subclasses override the steps they support
     def train_step(self, features):
-        pass
+        return None
 
     def infer_step(self, features):
-        pass
+        return None
 
     def debug_step(self, features):
-        pass
+        return None

@@ -1,11 +1,13 @@
-from os.path import dirname
+"""Trainer lookup: the yaml `trainer` block names a class of this package and carries its keyword arguments
+(interface of reference trainers/__init__.py:6-12)."""
+import os
 
 from msmctts.utils.utils import module_search
 
+_HERE = os.path.dirname(__file__)
+
 
 def build_trainer(config, model, num_gpus=1, rank=0):
-    """yaml `trainer._name` -> class (reference trainers/__init__.py:6-12)"""
-    kwargs = config.trainer.to_dict()
-    name = kwargs.pop("_name")
-    Trainer = module_search(name, dirname(__file__), "msmctts.trainers")
-    return Trainer(config, model, num_gpus=num_gpus, rank=rank, **kwargs)
+    options = dict(config.trainer.to_dict())
+    cls = module_search(options.pop("_name"), _HERE, "msmctts.trainers")
+    return cls(config, model, num_gpus=num_gpus, rank=rank, **options)

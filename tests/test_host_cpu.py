@@ -254,6 +254,14 @@ def test_trainer_loop_checkpoints_and_resumes(tmp_path):
     assert again.attempt_load_checkpoint() == 3                     # resumes after the saved iteration
     for a, b in zip(trainer.model.state_dict().values(), again.model.state_dict().values()):
         assert torch.equal(a, b)
+    # checkpoint -> task / sub-network (reference tasks/__init__.py: load_task, load_model; the predictor trainer
+    # loads its frozen autoencoder this way)
+    from msmctts.tasks import build_task as bt, load_model
+    ckpt = os.path.join(config.save_checkpoint_dir, "model_2")
+    ae = load_model("autoencoder", ckpt)
+    for k, v in trainer.model.autoencoder.state_dict().items():
+        assert torch.equal(ae.state_dict()[k], v), k
+    assert [n for n, _ in bt(checkpoint=ckpt, mode="infer").named_children()] == ["autoencoder", "discriminator"]
 
 
 def test_train_cli_fails_loudly_without_a_gpu(tmp_path):
