@@ -132,6 +132,13 @@ int msmc_reflect_pad_fold(const float* gpad, float* gx, int32_t B, int32_t H, in
 int msmc_vq_search(const float* z, int64_t ld_z, const float* embed, float* quant_raw, float* quant_st,
                    float* diff, int64_t* idx, int32_t n_rows, int32_t n_heads, int32_t dim,
                    int32_t n_embed, void* stream);
+/* EXPERIMENTAL (default off, MSMC_VQ_UMMA=1): the same search, results identical by construction, as a two-phase
+ * kernel -- all codewords scored on the tensor cores (tcgen05, 3xTF32), candidates within a provable margin of the
+ * row minimum re-scored with the exact sequential-fma arithmetic.  dim = 64, n_embed in {64, 128, 256}, <= 8 heads,
+ * ld_z a multiple of 4, 16-byte aligned pointers; MSMC_ERR_UNSUPPORTED otherwise. */
+int msmc_vq_search_umma(const float* z, int64_t ld_z, const float* embed, float* quant_raw, float* quant_st,
+                        float* diff, int64_t* idx, int32_t n_rows, int32_t n_heads, int32_t dim, int32_t n_embed,
+                        void* stream);
 /* EMA codebook update (modules.py:35-57).  row r = b*t + i is valid iff i < lengths[b].
  * Updates cluster_size (n_heads,n_embed), embed_avg and embed (n_heads,dim,n_embed) in place. */
 int msmc_vq_ema_update(const float* z, int64_t ld_z, const int64_t* idx, const int32_t* lengths,

@@ -16,6 +16,7 @@ from . import lib as L
 CONV_MATH = os.environ.get("MSMC_CONV_MATH", "3xtf32")
 UMMA_MIN_ROWS = 256
 USE_TAP_REUSE = os.environ.get("MSMC_TAP_REUSE", "1") != "0"
+VQ_UMMA = os.environ.get("MSMC_VQ_UMMA", "0") == "1"     # experimental: see csrc/vq_umma.cu
 
 ConvCfg = namedtuple("ConvCfg", "KH KW sh sw dh dw ph pw reflect transposed wstr Cd pre_slope post out_hw")
 # wstr = element strides of the weight tensor for (kh, kw, cs, cd), cs = channels of the op's INPUT
@@ -575,7 +576,11 @@ class _VQFn(torch.autograd.Function):
         q_st = torch.empty_like(q_raw)
         diff = torch.empty((n_rows, dim), dtype=torch.float32, device=z.device)
         idx = torch.empty((n_rows, n_heads), dtype=torch.int64, device=z.device)
-        L.call("msmc_vq_search", L.ptr(z2), C.c_int64(z2.stride(0)), L.ptr(embed), L.ptr(q_raw), L.ptr(q_st),
+        entry = "msmc_vq_search"
+        if VQ_UMMA and dim == 64 and K in (64, 128, 256) and n_heads <= 8 and z2.stride(0) % 4 == 0 \
+                and z2.data_ptr() % 16 == 0:
+            entry = "msmc_vq_search_umma"      # experimental two-phase tensor-core search (default off)
+        L.call(entry, L.ptr(z2), C.c_int64(z2.stride(0)), L.ptr(embed), L.ptr(q_raw), L.ptr(q_st),
                L.ptr(diff), L.ptr(idx), n_rows, n_heads, dim, K)
         ctx.save_for_backward(z2, q_raw)
         ctx.hd = (n_heads, dim)

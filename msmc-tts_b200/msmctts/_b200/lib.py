@@ -53,6 +53,7 @@ SIGNATURES = {
     "msmc_weight_norm_bwd": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
     "msmc_reflect_pad_fold": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "msmc_vq_search": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    "msmc_vq_search_umma": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "msmc_vq_ema_update": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _F, _F, _P, _P, _P, _P]),
     "msmc_vq_backward": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
     "msmc_vq_triple_loss": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _I32, _P]),
