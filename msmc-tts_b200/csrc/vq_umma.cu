@@ -30,6 +30,7 @@ constexpr int VU_DIM = 64;                   // dims per head (two K halves of 3
 constexpr int VU_PRODUCERS = 256;            // 8 producer / epilogue warps
 constexpr int VU_THREADS = VU_PRODUCERS + 32;  // + the MMA warp
 constexpr int VU_MAX_CAND = 4;               // candidates kept per row half before the exhaustive fallback
+constexpr int VU_DV_LD = VU_DIM + 1;         // padded row pitch of the (q - z)^2 tile: a warp's 32 rows hit 32 banks
 
 // A and B planes use different shared-memory layouts, hence different descriptor high words
 __device__ __forceinline__ void umma_tf32_kmaj_a_mnmaj_b(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
@@ -80,7 +81,7 @@ __device__ __forceinline__ void emit_row_half(const float (&zr)[VU_DIM], const f
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const float dq = q[j] - zr[D0 + j];
-    dv[r * VU_DIM + D0 + j] = __fmul_rn(dq, dq);      // no fma contraction with the head sum
+    dv[r * VU_DV_LD + D0 + j] = __fmul_rn(dq, dq);    // no fma contraction with the head sum
   }
 }
 
@@ -108,7 +109,7 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ee_max + 2);
   uint64_t* accum_bar = full_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-  float* dv = reinterpret_cast<float*>(sA);      // [128][64] per-row (q - z)^2 of this head; aliases A after the MMAs
+  float* dv = reinterpret_cast<float*>(sA);      // [128][65] per-row (q - z)^2 of this head; aliases A after the MMAs
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_heads = gridDim.y, h = blockIdx.y;
@@ -238,12 +239,13 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
 
     if (chalf == 0) {
       // the row's owner decides: one candidate -> done; a few -> exact re-score in ascending index order (lowest
-      // index wins ties, like the exhaustive search); too many to have been recorded -> exhaustive exact search
+      // index wins ties, like the exhaustive search); too many to have been recorded, or none (NaN input) ->
+      // exhaustive exact search
       const int c_lo = cand_cnt[r], c_hi = cand_cnt[VU_ROWS + r];
       int best_k;
       if (c_lo + c_hi == 1) {
         best_k = c_lo ? cand_idx[r * VU_MAX_CAND] : cand_idx[(VU_ROWS + r) * VU_MAX_CAND];
-      } else if (c_lo <= VU_MAX_CAND && c_hi <= VU_MAX_CAND) {
+      } else if (c_lo + c_hi >= 2 && c_lo <= VU_MAX_CAND && c_hi <= VU_MAX_CAND) {
         float bd = INFINITY;
         best_k = 0x7fffffff;
         for (int half2 = 0; half2 < 2; ++half2) {
@@ -310,8 +312,8 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
   for (int e = tid; e < VU_ROWS * VU_DIM; e += VU_THREADS) {
     const int ri = e / VU_DIM, d_ = e - ri * VU_DIM;
     if (ri < rows_here && (ri % n_heads) == h) {
-      float acc = *cluster.map_shared_rank(dv + ri * VU_DIM + d_, 0);
-      for (int hh = 1; hh < n_heads; ++hh) acc = __fadd_rn(acc, *cluster.map_shared_rank(dv + ri * VU_DIM + d_, hh));
+      float acc = *cluster.map_shared_rank(dv + ri * VU_DV_LD + d_, 0);
+      for (int hh = 1; hh < n_heads; ++hh) acc = __fadd_rn(acc, *cluster.map_shared_rank(dv + ri * VU_DV_LD + d_, hh));
       diff[(int64_t)(row0 + ri) * VU_DIM + d_] = acc * inv_heads;
     }
   }
