@@ -204,13 +204,21 @@ int msmc_log_clamp_fwd(const float* x, float* y, int64_t n, float clip, void* st
 int msmc_log_clamp_bwd(const float* gy, const float* x, float* gx, int64_t n, float clip, void* stream);
 
 /* fused multi-tensor Adam / AdamW step with torch.optim semantics (reference trainers/optimizers/__init__.py:9-30
- * builds torch.optim.Adam / AdamW per child module).  table = device array [4][n_tensors] of pointers
- * (param, grad, exp_avg, exp_avg_sq), sizes[n_tensors] element counts, one CTA per (chunk_tensor[c], chunk_index[c])
- * chunk of msmc_adam_chunk_elems() elements.  lr and step are DEVICE scalars (step = already incremented count) */
+ * builds torch.optim.Adam / AdamW per child module) with the global gradient-norm clip of the trainer folded in
+ * (reference trainers/msmctts_trainer.py:203-207: clip_grad_norm_ followed by optimizer.step()).
+ * table = device array [4][n_tensors] of pointers (param, grad, exp_avg, exp_avg_sq), sizes[n_tensors] element
+ * counts, one CTA per (chunk_tensor[c], chunk_index[c]) chunk of msmc_adam_chunk_elems() elements.
+ * steps = DEVICE vector of per-parameter step counters, step_index[t] = slot of tensor t: the call advances the
+ * counter of every listed tensor by one (torch advances a parameter's step only when it has a gradient) and uses the
+ * advanced value for the bias correction.  lr is a DEVICE scalar.
+ * max_norm > 0 (needs partial = n_chunks floats of workspace): gradients are scaled in place by
+ * min(1, max_norm / (total_norm + 1e-6)) before the update, total_norm = l2 norm over all listed gradients, also
+ * written to norm_out[0] when non-null (torch.nn.utils.clip_grad_norm_ semantics).  Two launches. */
 int msmc_adam_chunk_elems(void);
 int msmc_adam_multi(const uint64_t* table, int32_t n_tensors, const int64_t* sizes, const int32_t* chunk_tensor,
-                    const int32_t* chunk_index, int32_t n_chunks, const float* lr, const float* step, float beta1,
-                    float beta2, float eps, float weight_decay, int32_t decoupled, void* stream);
+                    const int32_t* chunk_index, int32_t n_chunks, const int32_t* step_index, float* steps,
+                    float* partial, float max_norm, float* norm_out, const float* lr, float beta1, float beta2,
+                    float eps, float weight_decay, int32_t decoupled, void* stream);
 /* feature-matching loss over a list of tensor pairs (reference trainers/msmctts_trainer.py:186-190: the sum of 55
  * F.l1_loss(fake_fmap, real_fmap) terms): out[0] = sum_t mean|a_t - b_t|.  table = device array [2][n_tensors] of
  * pointers (a, b) ([3][n_tensors] with the gradient buffers ga for _bwd), chunks of msmc_l1_chunk_elems() elements,

@@ -16,10 +16,17 @@ extern "C" int msmc_version(void) { return 100; }
 extern "C" int msmc_num_sms(void) { return msmc::num_sms(); }
 
 // ------------------------------------------------------------------------------------------------
-// Fused multi-tensor Adam / AdamW step.  torch's capturable foreach path spends one tiny kernel per parameter on
-// the device-resident step size (lr / bias_correction1: ~1.2k launches per train step here) plus a dozen
-// multi-tensor passes; this is one launch per optimizer: block = one 16k-element chunk of one tensor, pointers
-// come from a device table, lr and the (already incremented) step count are device scalars so the launch is
+// Fused multi-tensor Adam / AdamW step with the global gradient-norm clip folded in (reference
+// trainers/msmctts_trainer.py:203-207 clip_grad_norm_ + optimizers/__init__.py:53-78 step).  torch's capturable
+// foreach path spends one tiny kernel per parameter on the device-resident step size (~1.2k launches per train
+// step here) plus a dozen multi-tensor passes, and clip_grad_norm_ another ~10; this is TWO launches per optimizer:
+//   adam_prepare_kernel : per 16k-element chunk the sum of squares of the gradient (fixed order) -> partial[chunk];
+//                         the first chunk of every tensor also advances THAT tensor's step counter (torch advances
+//                         a parameter's step only when it has a gradient: counters are per parameter).
+//   adam_multi_kernel   : every block re-reduces partial[] in a fixed order (a few KB from L2) into the total norm,
+//                         forms clip = min(1, max_norm / (norm + 1e-6)) exactly like torch.nn.utils.clip_grad_norm_,
+//                         and applies the update with the clipped gradient (written back, as clip_grad_norm_ does).
+// Pointers come from a device table; lr, the step counters and the norm are device scalars, so the launches are
 // CUDA-graph replayable.
 // ------------------------------------------------------------------------------------------------
 namespace msmc {
@@ -27,24 +34,86 @@ namespace {
 constexpr int ADAM_CHUNK = 16384;
 constexpr int ADAM_THREADS = 256;
 
+__device__ __forceinline__ float adam_block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (ADAM_THREADS / 32) ? sh[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+  }
+  return t;   // valid in warp 0
+}
+
+__global__ void __launch_bounds__(ADAM_THREADS) adam_prepare_kernel(
+    const unsigned long long* __restrict__ table, int n_tensors, const long long* __restrict__ sizes,
+    const int* __restrict__ chunk_tensor, const int* __restrict__ chunk_index, const int* __restrict__ step_index,
+    float* __restrict__ steps, float* __restrict__ partial, int want_norm) {
+  __shared__ float sh[ADAM_THREADS / 32];
+  const int t = chunk_tensor[blockIdx.x];
+  const int ci = chunk_index[blockIdx.x];
+  if (ci == 0 && threadIdx.x == 0) steps[step_index[t]] += 1.f;
+  if (!want_norm) return;
+  const long long beg = (long long)ci * ADAM_CHUNK;
+  const long long n = sizes[t];
+  const long long end = beg + ADAM_CHUNK < n ? beg + ADAM_CHUNK : n;
+  const float* __restrict__ g = reinterpret_cast<const float*>(table[n_tensors + t]);
+  float acc = 0.f;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    const long long end4 = beg + ((end - beg) & ~3LL);
+    for (long long i = beg + 4LL * threadIdx.x; i < end4; i += 4LL * ADAM_THREADS) {
+      const float4 x = *reinterpret_cast<const float4*>(g + i);
+      acc += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+    }
+    for (long long i = end4 + threadIdx.x; i < end; i += ADAM_THREADS) acc += g[i] * g[i];
+  } else {
+    for (long long i = beg + threadIdx.x; i < end; i += ADAM_THREADS) acc += g[i] * g[i];
+  }
+  const float tot = adam_block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
 __global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(
     const unsigned long long* __restrict__ table, int n_tensors, const long long* __restrict__ sizes,
-    const int* __restrict__ chunk_tensor, const int* __restrict__ chunk_index, const float* __restrict__ lr_p,
-    const float* __restrict__ step_p, float beta1, float beta2, float eps, float weight_decay, int decoupled) {
+    const int* __restrict__ chunk_tensor, const int* __restrict__ chunk_index, const int* __restrict__ step_index,
+    const float* __restrict__ steps, const float* __restrict__ partial, int n_chunks, float max_norm,
+    float* __restrict__ norm_out, const float* __restrict__ lr_p, float beta1, float beta2, float eps,
+    float weight_decay, int decoupled) {
+  __shared__ float sh[ADAM_THREADS / 32];
+  __shared__ float s_clip;
   const int t = chunk_tensor[blockIdx.x];
   const long long beg = (long long)chunk_index[blockIdx.x] * ADAM_CHUNK;
   const long long n = sizes[t];
   const long long end = beg + ADAM_CHUNK < n ? beg + ADAM_CHUNK : n;
   float* __restrict__ p = reinterpret_cast<float*>(table[t]);
-  const float* __restrict__ g = reinterpret_cast<const float*>(table[n_tensors + t]);
+  float* __restrict__ g = reinterpret_cast<float*>(table[n_tensors + t]);
   float* __restrict__ m = reinterpret_cast<float*>(table[2 * n_tensors + t]);
   float* __restrict__ v = reinterpret_cast<float*>(table[3 * n_tensors + t]);
-  const float lr = *lr_p, step = *step_p;
+  float clip = 1.f;
+  if (partial != nullptr) {
+    // identical order in every block -> every block derives the identical coefficient
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n_chunks; i += ADAM_THREADS) acc += partial[i];
+    const float tot = adam_block_sum(acc, sh);
+    if (threadIdx.x == 0) {
+      const float norm = sqrtf(tot);
+      const float c = max_norm / (norm + 1e-6f);
+      s_clip = c < 1.f ? c : 1.f;
+      if (blockIdx.x == 0 && norm_out) *norm_out = norm;
+    }
+    __syncthreads();
+    clip = s_clip;
+  }
+  const bool write_g = partial != nullptr;
+  const float lr = *lr_p, step = steps[step_index[t]];
   const float bc1 = 1.f - powf(beta1, step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
   const float step_size = lr / bc1;
   const float decay = 1.f - lr * weight_decay;
-  auto upd = [&](float& pw, float gw, float& mw, float& vw) {
+  auto upd = [&](float& pw, float& gw_io, float& mw, float& vw) {
+    float gw = gw_io * clip;                    // clip_grad_norm_: grad.mul_(clip_coef_clamped)
+    gw_io = gw;
     if (decoupled) pw *= decay;                 // AdamW: param.mul_(1 - lr * wd)
     else gw = fmaf(weight_decay, pw, gw);       // Adam : grad + wd * param
     mw = mw + (gw - mw) * (1.f - beta1);        // exp_avg.lerp_(grad, 1 - beta1)
@@ -58,7 +127,7 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(
     const long long end4 = beg + ((end - beg) & ~3LL);
     for (long long i = beg + 4LL * threadIdx.x; i < end4; i += 4LL * ADAM_THREADS) {
       float4 pw = *reinterpret_cast<float4*>(p + i);
-      const float4 gw = *reinterpret_cast<const float4*>(g + i);
+      float4 gw = *reinterpret_cast<const float4*>(g + i);
       float4 mw = *reinterpret_cast<float4*>(m + i);
       float4 vw = *reinterpret_cast<float4*>(v + i);
       upd(pw.x, gw.x, mw.x, vw.x); upd(pw.y, gw.y, mw.y, vw.y);
@@ -66,10 +135,19 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(
       *reinterpret_cast<float4*>(p + i) = pw;
       *reinterpret_cast<float4*>(m + i) = mw;
       *reinterpret_cast<float4*>(v + i) = vw;
+      if (write_g) *reinterpret_cast<float4*>(g + i) = gw;
     }
-    for (long long i = end4 + threadIdx.x; i < end; i += ADAM_THREADS) upd(p[i], g[i], m[i], v[i]);
+    for (long long i = end4 + threadIdx.x; i < end; i += ADAM_THREADS) {
+      float gw = g[i];
+      upd(p[i], gw, m[i], v[i]);
+      if (write_g) g[i] = gw;
+    }
   } else {
-    for (long long i = beg + threadIdx.x; i < end; i += ADAM_THREADS) upd(p[i], g[i], m[i], v[i]);
+    for (long long i = beg + threadIdx.x; i < end; i += ADAM_THREADS) {
+      float gw = g[i];
+      upd(p[i], gw, m[i], v[i]);
+      if (write_g) g[i] = gw;
+    }
   }
 }
 }  // namespace
@@ -79,12 +157,21 @@ extern "C" int msmc_adam_chunk_elems(void) { return msmc::ADAM_CHUNK; }
 
 extern "C" int msmc_adam_multi(const uint64_t* table, int32_t n_tensors, const int64_t* sizes,
                                const int32_t* chunk_tensor, const int32_t* chunk_index, int32_t n_chunks,
-                               const float* lr, const float* step, float beta1, float beta2, float eps,
+                               const int32_t* step_index, float* steps, float* partial, float max_norm,
+                               float* norm_out, const float* lr, float beta1, float beta2, float eps,
                                float weight_decay, int32_t decoupled, void* stream) {
-  MSMC_REQUIRE(table && sizes && chunk_tensor && chunk_index && lr && step && n_tensors > 0 && n_chunks > 0);
-  msmc::adam_multi_kernel<<<n_chunks, msmc::ADAM_THREADS, 0, (cudaStream_t)stream>>>(
+  MSMC_REQUIRE(table && sizes && chunk_tensor && chunk_index && step_index && steps && lr && n_tensors > 0 &&
+               n_chunks > 0);
+  MSMC_REQUIRE(partial != nullptr || max_norm <= 0.f);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool clip = partial != nullptr && max_norm > 0.f;
+  msmc::adam_prepare_kernel<<<n_chunks, msmc::ADAM_THREADS, 0, st>>>(
       reinterpret_cast<const unsigned long long*>(table), n_tensors, reinterpret_cast<const long long*>(sizes),
-      chunk_tensor, chunk_index, lr, step, beta1, beta2, eps, weight_decay, decoupled);
+      chunk_tensor, chunk_index, step_index, steps, partial, clip ? 1 : 0);
+  msmc::adam_multi_kernel<<<n_chunks, msmc::ADAM_THREADS, 0, st>>>(
+      reinterpret_cast<const unsigned long long*>(table), n_tensors, reinterpret_cast<const long long*>(sizes),
+      chunk_tensor, chunk_index, step_index, steps, clip ? partial : nullptr, n_chunks, max_norm, norm_out, lr,
+      beta1, beta2, eps, weight_decay, decoupled);
   MSMC_CHECK_LAUNCH();
   return MSMC_OK;
 }

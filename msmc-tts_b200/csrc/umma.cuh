@@ -17,6 +17,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok;
+  // watchdog: a protocol bug must surface as a launch failure (trap), never as a hung GPU.  try_wait suspends the
+  // thread for a bounded, implementation-defined time per probe, so 2^24 failed probes is seconds, not a step.
+  uint32_t spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -25,6 +28,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(addr), "r"(parity)
         : "memory");
+    if (!ok && ++spins == (1u << 24)) __trap();
   } while (!ok);
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {

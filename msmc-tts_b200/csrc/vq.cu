@@ -118,6 +118,9 @@ vq_search_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restr
           const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
           if (ob < best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
         }
+        // a row holding NaN / Inf makes every distance NaN and no candidate wins: the reference's (-dist).max(1)
+        // then returns index 0 (first NaN); without this the sentinel would index far outside the codebook
+        if ((unsigned)best_k >= (unsigned)KP) best_k = 0;
         if (row < row_end) {
           if (lane == 0) idx[(int64_t)row * n_heads + h] = (int64_t)best_k;
 #pragma unroll
@@ -289,6 +292,9 @@ vq_search_cluster_kernel(const float* __restrict__ z, int64_t ld_z, const float*
           const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
           if (ob < best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
         }
+        // a row holding NaN / Inf makes every distance NaN and no candidate wins: the reference's (-dist).max(1)
+        // then returns index 0 (first NaN); without this the sentinel would index far outside the codebook
+        if ((unsigned)best_k >= (unsigned)KP) best_k = 0;
         if (row < row_end) {
           if (lane == 0) idx[(int64_t)row * n_heads + h] = (int64_t)best_k;
 #pragma unroll
@@ -459,6 +465,9 @@ vq_search_bulk_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
           const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
           if (ob < best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
         }
+        // a row holding NaN / Inf makes every distance NaN and no candidate wins: the reference's (-dist).max(1)
+        // then returns index 0 (first NaN); without this the sentinel would index far outside the codebook
+        if ((unsigned)best_k >= (unsigned)KP) best_k = 0;
         if (row < row_end) {
           if (lane == 0) idx[(int64_t)row * n_heads + h] = (int64_t)best_k;
 #pragma unroll

@@ -70,8 +70,7 @@ SIGNATURES = {
     "msmc_log_clamp_fwd": (C.c_int, [_P, _P, _I64, _F, _P]),
     "msmc_log_clamp_bwd": (C.c_int, [_P, _P, _P, _I64, _F, _P]),
     "msmc_adam_chunk_elems": (C.c_int, []),
-    "msmc_adam_multi": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float,
-                                  _I32, _P]),
+    "msmc_adam_multi": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, _P, _P, _F, _P, _P, _F, _F, _F, _F, _I32, _P]),
     "msmc_l1_chunk_elems": (C.c_int, []),
     "msmc_l1_multi_fwd": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, _P, _P]),
     "msmc_l1_multi_bwd": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, _P]),
@@ -86,7 +85,7 @@ SIGNATURES = {
 _STATUS = {1: "MSMC_ERR_BAD_ARG", 2: "MSMC_ERR_LAUNCH", 3: "MSMC_ERR_UNSUPPORTED"}
 _lib = None
 # kernels each entry point launches (bench.py's `gpu_launches` is the sum over the timed region)
-KERNELS_PER_CALL = {"msmc_l1_multi_fwd": 2, "msmc_conv_wgrad": 2, "msmc_conv_wgrad_umma": 2, "msmc_vq_ema_update": 2, "msmc_attention_bwd": 2,
+KERNELS_PER_CALL = {"msmc_l1_multi_fwd": 2, "msmc_adam_multi": 2, "msmc_conv_wgrad": 2, "msmc_conv_wgrad_umma": 2, "msmc_vq_ema_update": 2, "msmc_attention_bwd": 2,
                     "msmc_add_layernorm_bwd": 2}
 launch_count = 0   # kernels launched through the C-ABI so far
 _profile = None    # when a list: (name, meta, start_event, end_event) per call, for bench.py's roofline pass

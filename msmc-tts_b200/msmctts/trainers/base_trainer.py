@@ -64,6 +64,7 @@ class BaseTrainer(object):
             for batch in loader:
                 lr_scheduler.step(self.optimizer, iteration)
                 batch = to_model(batch)
+                self.optimizer.zero_grad()         # reference base_trainer.py:84-85 (set_to_none: no launches)
                 log = self.train_step(batch, iteration)
                 logger.log(iteration, log)
                 if self.rank == 0 and iteration > 0 and iteration % self.config.iters_per_checkpoint == 0:

@@ -99,8 +99,8 @@ def _frozen(module):
 class VQGANTrainer(BaseTrainer):
     def __init__(self, config, model, num_gpus=1, rank=0, warmup_steps=0, lambda_frame=1.0,
                  eval_inteval_iters=1000, grad_clip_thresh=1.0, sample_lengths=24000, lambda_vq=1, lambda_pr=1,
-                 lambda_fm=2, lambda_stft=45, stft_loss_func="mel_loss", stft_loss_config=None, cuda_graph=False,
-                 reference_schedule=False):
+                 lambda_fm=2, lambda_stft=45, stft_loss_func="mel_loss", stft_loss_config=None, cuda_graph=None,
+                 reference_schedule=False, max_graphs=4, graph_bucket_frames=0):
         super().__init__(config, model, num_gpus, rank)
         # reference_schedule=False (default) keeps every loss value and every parameter update of the reference's
         # step but drops work whose result the reference discards:
@@ -112,9 +112,15 @@ class VQGANTrainer(BaseTrainer):
         # reference_schedule=True replays the reference's exact launch schedule (4 separate D passes, D gradients
         # computed in the G step).
         self.reference_schedule = bool(reference_schedule)
-        # cuda_graph=True: the sync-free step body is captured once per (shape, phase) into a CUDA graph and
-        # replayed -- ~2.6k kernel launches and all Python/autograd dispatch collapse into one graph launch
-        self.use_cuda_graph = bool(cuda_graph)
+        # cuda_graph: the sync-free step body is captured once per (shape, phase) into a CUDA graph and replayed --
+        # ~2k kernel launches and all Python/autograd dispatch collapse into one graph launch.  Default (None) = on
+        # whenever the model lives on a CUDA device, so `train.py -c <reference yaml>` (no such key) gets the graphed
+        # step.  At most `max_graphs` shapes are captured (each holds its own activation pool); further shapes run the
+        # eager step.  graph_bucket_frames > 0 pads every batch on the right (mel with the dataset's pad value, wav
+        # with zeros; lengths unchanged, so every masked quantity is unaffected) to a multiple of that many frames so
+        # that variable-length batches share a few graphs.
+        self.use_cuda_graph = bool(next(model.parameters()).is_cuda) if cuda_graph is None else bool(cuda_graph)
+        self.max_graphs, self.graph_bucket_frames = int(max_graphs), int(graph_bucket_frames)
         self._graphs = {}
         self.lambda_frame, self.warmup_steps = lambda_frame, warmup_steps
         self.frameshift = self.config.dataset.frameshift[self.config.dataset.feature.index("mel")]
@@ -167,8 +173,21 @@ class VQGANTrainer(BaseTrainer):
 
     def _graphed_step(self, mel, mel_length, wav, starts, warmup, gan):
         """CUDA-graph replay of `_step` on static input buffers (one graph per input shape and phase)."""
+        if self.graph_bucket_frames > 0:
+            T, Tb = mel.shape[1], -(-mel.shape[1] // self.graph_bucket_frames) * self.graph_bucket_frames
+            if Tb != T:
+                pad_value = -4.0
+                pv = self.config.dataset.get("padding_value", None)
+                if isinstance(pv, (list, tuple)):       # one value per feature (reference yaml: [-4, 0])
+                    pad_value = float(pv[list(self.config.dataset.feature).index("mel")])
+                mel = F.pad(mel, (0, 0, 0, Tb - T), value=pad_value)
+                if wav is not None:
+                    wav = F.pad(wav, (0, 0, 0, (Tb - T) * self.frameshift) if wav.dim() == 3
+                                else (0, (Tb - T) * self.frameshift))
         key = (tuple(mel.shape), None if wav is None else tuple(wav.shape), warmup, gan)
         st = self._graphs.get(key)
+        if st is None and len(self._graphs) >= self.max_graphs:
+            return self._step(mel, mel_length, wav, starts, warmup=warmup, gan=gan)
         if st is None:
             st = {"n": 0, "inp": [None if t is None else torch.empty_like(t) for t in (mel, mel_length, wav, starts)]}
             self._graphs[key] = st
@@ -193,6 +212,18 @@ class VQGANTrainer(BaseTrainer):
             st["graph"] = graph
         st["graph"].replay()
         return st["out"]
+
+    def release_graphs(self):
+        """drop the captured graphs (and their private memory pools).  Must run before the NCCL communicator is
+        destroyed when the graphs hold captured all-reduces: destroy_process_group() otherwise never returns."""
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        for st in self._graphs.values():
+            st.pop("graph", None)
+            st.pop("out", None)
+        self._graphs = {}
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
 
     def _step(self, mel, mel_length, wav, starts, warmup, gan):
         if mel.is_cuda:
@@ -279,8 +310,8 @@ class VQGANTrainer(BaseTrainer):
         self.optimizer.zero_grad(["autoencoder"])
         only = None if (self.reference_schedule or not gan) else list(self.model.autoencoder.parameters())
         self.backward(g_loss, "autoencoder", inputs=only)
-        nn.utils.clip_grad_norm_(self.model.autoencoder.parameters(), self.grad_clip_thresh)
-        self.optimizer.step(["autoencoder"])
+        # clip_grad_norm_ + AdamW (reference :203-207) in the optimizer's two fused launches
+        self.optimizer.step(["autoencoder"], max_grad_norm=self.grad_clip_thresh)
         if prefetch is not None:
             torch.cuda.current_stream().wait_stream(prefetch)      # join the side stream (graph capture needs it)
         return {"loss": {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}}
@@ -315,8 +346,9 @@ class PredictorTrainer(BaseTrainer):
         self.optimizer.zero_grad(["predictor"])
         self.backward(losses["total_loss"], "predictor")
         if self.grad_clip_thresh is not None:
-            losses["grad_norm"] = nn.utils.clip_grad_norm_(self.model.predictor.parameters(), self.grad_clip_thresh)
-        self.optimizer.step(["predictor"])
+            losses["grad_norm"] = self.optimizer.step(["predictor"], max_grad_norm=self.grad_clip_thresh)
+        else:
+            self.optimizer.step(["predictor"])
         return {"loss": {k: (v.detach() if torch.is_tensor(v) else v) for k, v in losses.items()}}
 
     def build_autoencoder(self, autoencoder=None):

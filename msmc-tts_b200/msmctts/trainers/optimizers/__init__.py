@@ -32,7 +32,10 @@ def build_optimizer(model, config):
             assert hasattr(config, "_default"), "Both {} and _default not found".format(module_name)
             module_config = config._default
         configs[module_name] = module_config
-        parameters = [p for p in module.parameters() if p.requires_grad]
+        # every parameter, frozen ones included, exactly like the reference (:38): param-group sizes then match the
+        # reference's optimizer checkpoints whatever `config.freeze` says; parameters without a gradient are skipped
+        # by the step (torch and FusedAdam alike)
+        parameters = list(module.parameters())
         if hasattr(module_config, "parameters"):
             parameters = []
             for name, p in module.named_parameters():
@@ -65,6 +68,19 @@ class Optimizer(object):
         for key in self._names(names):
             self.optimizers[key].zero_grad(set_to_none=True)
 
-    def step(self, names=None):
+    def step(self, names=None, max_grad_norm=None):
+        """max_grad_norm: clip the global gradient norm of each named optimizer's parameters first (reference
+        trainers/msmctts_trainer.py:203-207); fused into the update launches on CUDA.  Returns the norm(s)."""
+        norms = []
         for key in self._names(names):
-            self.optimizers[key].step()
+            opt = self.optimizers[key]
+            if max_grad_norm is None:
+                opt.step()
+            elif hasattr(opt, "last_grad_norm"):
+                opt.step(max_grad_norm=max_grad_norm)
+                norms.append(opt.last_grad_norm)
+            else:
+                params = [p for g in opt.param_groups for p in g["params"]]
+                norms.append(torch.nn.utils.clip_grad_norm_(params, max_grad_norm))
+                opt.step()
+        return norms[0] if len(norms) == 1 else norms

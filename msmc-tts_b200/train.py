@@ -25,6 +25,15 @@ def train(config, num_gpus, rank, group_name):
     task = build_task(config, "train")
     trainer = build_trainer(config, task, num_gpus=num_gpus, rank=rank)
     trainer.train()
+    if num_gpus > 1:
+        # captured graphs hold NCCL all-reduce nodes: they go before the communicator (destroy_process_group() after
+        # graph-captured collectives otherwise never returns)
+        import torch.distributed as dist
+        if hasattr(trainer, "release_graphs"):
+            trainer.release_graphs()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
     print("Training done!")
 
 

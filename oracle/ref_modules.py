@@ -438,11 +438,11 @@ def torch_stft_transform(x, hop, sample_rate=24000, domain="double", mel_scale=T
     """utils/audio.py:398-419 TorchSTFT.transform with fft=win=4*hop, normalized=True (discriminator.py:86-90)
     followed by MelScale (audio.py:348-376) with n_mels == n_freqs.  x (B, L) -> (B, 2F | F, frames)"""
     n_fft = hop * 4
-    st = stft_real(x, n_fft, hop, n_fft, torch.hann_window(n_fft), normalized=True)
+    st = stft_real(x, n_fft, hop, n_fft, torch.hann_window(n_fft, device=x.device), normalized=True)
     mag = torch.sqrt(torch.clamp(st[..., 0] ** 2 + st[..., 1] ** 2, min=1e-7))
     if mel_scale:
         nf = n_fft // 2 + 1
-        fb = create_fb_matrix(nf, 0.0, float(sample_rate // 2), nf, sample_rate)
+        fb = create_fb_matrix(nf, 0.0, float(sample_rate // 2), nf, sample_rate).to(mag.device)
         mag = torch.matmul(mag.transpose(1, 2), fb).transpose(1, 2)
     if domain == "linear":
         return mag
@@ -547,10 +547,10 @@ def slaney_mel_filterbank(sr, n_fft, n_mels, fmin, fmax):
 
 def mel_spectrogram(y, fft_size, hop_size, win_size, sample_rate, num_mels):
     """trainers/criterions/stft_loss.py:78-107 MelLoss.mel_spectrogram"""
-    basis = slaney_mel_filterbank(sample_rate, fft_size, num_mels, 0, sample_rate // 2)
+    basis = slaney_mel_filterbank(sample_rate, fft_size, num_mels, 0, sample_rate // 2).to(y.device)
     pad = int((fft_size - hop_size) / 2)
     y = F.pad(y.unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)
-    spec = stft_real(y, fft_size, hop_size, win_size, torch.hann_window(win_size), center=False)
+    spec = stft_real(y, fft_size, hop_size, win_size, torch.hann_window(win_size, device=y.device), center=False)
     spec = torch.sqrt(spec.pow(2).sum(-1) + 1e-9)
     spec = torch.matmul(basis, spec)
     return torch.log(torch.clamp(spec, min=1e-5))

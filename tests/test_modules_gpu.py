@@ -186,18 +186,10 @@ def _csmsc_cfg(K):
     return cfg
 
 
-@pytest.mark.parametrize("K", [64, 256])
-def test_full_size_autoencoder_and_discriminator_vs_oracle(K):
-    """CSMSC shapes (B=16, T=240, window 40 frames -> 12000 samples), seeded random weights, eval-mode numerics
-    (dropout off) with the EMA update on: CUDA modules vs the CPU oracle on the SAME state_dict."""
-    from oracle import ref_modules as O
-    from msmctts.networks.hifigan import UnivNetDiscriminator
+def _full_size_ae(K):
     cfg = _csmsc_cfg(K)
     torch.manual_seed(1234)
     ae = _build_ae(cfg["autoencoder"])
-    for k, p in ae.named_parameters():
-        if k.startswith("decoder.") and k.endswith("weight_g"):
-            p.data.mul_(1.0)
     for pr in ae.quantizer.predictor:
         pr.enc.drop.p = 0.0
     for mod in ae.modules():       # dropout off everywhere so both sides are deterministic
@@ -214,34 +206,93 @@ def test_full_size_autoencoder_and_discriminator_vs_oracle(K):
     mel = mel * (torch.arange(T).view(1, -1, 1) < length.view(-1, 1, 1)) + \
         (-4.0) * (torch.arange(T).view(1, -1, 1) >= length.view(-1, 1, 1))
     window = [(int(min(100, l - 40)), int(min(100, l - 40)) + 40) for l in length.tolist()]
+    return cfg, ae, sd_cpu, mel, length, window
+
+
+@pytest.mark.parametrize("K", [64, 256])
+def test_full_size_autoencoder_forward_backward_vs_oracle(K):
+    """CSMSC shapes (B=16, T=240, window 40 frames -> 12000 samples), seeded random weights, dropout off, EMA update
+    on: CUDA autoencoder vs the CPU oracle on the SAME state_dict -- forward values, EMA buffers AND every parameter
+    gradient (the full-size weight-gradient / data-gradient kernel variants the bench launches).
+    VQ indices are bit-exact on identical z; upstream of the quantiser the two sides differ by fp32 summation order
+    (~1e-6 relative), so a vanishingly rare flip is tolerated -- but never silently: samples containing a flip are
+    dropped from BOTH sides' loss (samples are independent: no batch statistics anywhere), everything else is still
+    compared."""
+    from oracle import ref_modules as O
+    cfg, ae, sd_cpu, mel, length, window = _full_size_ae(K)
+    B = mel.shape[0]
     ae.to(DEV).train()
     out = ae(mel.to(DEV), length.to(DEV), warmup=False, window=window)
     ocfg = copy.deepcopy(cfg["autoencoder"])
-    with torch.no_grad():
-        ref = O.msmcvqgan_forward(sd_cpu, ocfg, mel, length, False, window, training=True, use_dropout=False)
-    mism = sum(int((a.cpu() != b).sum()) for a, b in zip(out["encoder_indices"], ref["encoder_indices"]))
-    total = sum(b.numel() for b in ref["encoder_indices"])
-    # indices are bit-exact on identical z; upstream of the quantiser the two sides differ by fp32 summation order
-    # (~1e-6 relative), so count flips instead of assuming none and require them to be vanishingly rare
+    sd_ref = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and
+                  k.split(".")[-1] not in ("embed", "embed_avg", "cluster_size") and not k.endswith("position.weight")
+                  else v.clone()) for k, v in sd_cpu.items()}
+    ref = O.msmcvqgan_forward(sd_ref, ocfg, mel, length, False, window, training=True, use_dropout=False)
+    flipped = torch.zeros(B, dtype=torch.bool)
+    mism = total = 0
+    for a, b in zip(out["encoder_indices"], ref["encoder_indices"]):
+        ne = (a.cpu() != b).reshape(B, -1)
+        flipped |= ne.any(dim=1)
+        mism += int(ne.sum())
+        total += b.numel()
     assert mism <= max(2, total // 5000), "index mismatches %d / %d" % (mism, total)
-    if mism == 0:
-        close(out["decoder_outputs"], ref["decoder_outputs"], tol=2e-4, msg="wav")
-        close(out["mel_outputs"], ref["mel_outputs"], tol=2e-4, msg="mel")
-        sd_gpu = ae.state_dict()
-        for k in sd_cpu:
-            if k.split(".")[-1] in ("embed", "embed_avg", "cluster_size"):
-                close(sd_gpu[k], sd_cpu[k], tol=1e-4, msg="EMA " + k)
-    # discriminator on a fixed waveform
+    keep = ~flipped
+    assert int(keep.sum()) >= B - 2
+    close(out["decoder_outputs"][keep.to(DEV)], ref["decoder_outputs"][keep], tol=2e-4, msg="wav")
+    close(out["mel_outputs"][keep.to(DEV)], ref["mel_outputs"][keep], tol=2e-4, msg="mel")
+    sd_gpu = ae.state_dict()
+    for k in sd_cpu:
+        if k.split(".")[-1] in ("embed", "embed_avg", "cluster_size"):
+            # the oracle's EMA ran in place on sd_ref; one flipped row moves a count by 0.01 -> looser when flips exist
+            close(sd_gpu[k], sd_ref[k], tol=1e-4 if mism == 0 else 5e-2, msg="EMA " + k)
+    # ---- full-size backward: one scalar over every output, flipped samples weighted out on both sides
+    gen = torch.Generator().manual_seed(7)
+    w_wav = torch.randn(ref["decoder_outputs"].shape, generator=gen)
+    w_mel = torch.randn(ref["mel_outputs"].shape, generator=gen) * 0.1
+    kf = keep.float()
+
+    def scalar(o, dev):
+        k3 = kf.to(dev).view(-1, 1, 1)
+        t = (o["decoder_outputs"] * w_wav.to(dev) * k3).sum() + (o["mel_outputs"] * w_mel.to(dev) * k3).sum()
+        for d in o["encoder_diffs"]:
+            t = t + (d * k3).sum() * 0.25
+        return t
+    scalar(out, DEV).backward()
+    scalar(ref, "cpu").backward()
+    ref_grads = {k: v.grad for k, v in sd_ref.items() if getattr(v, "grad", None) is not None}
+    assert len(ref_grads) > 300
+    check_grads(ae, ref_grads, tol=1e-3)
+
+
+def test_full_size_discriminator_forward_backward_vs_oracle():
+    """UnivNet MRD + MPD at the bench's own D-step shape -- cat(fake, real) = (32, 12000) -- vs the CPU oracle:
+    10 scores, 55 feature maps, the waveform gradient and every parameter gradient (3x3 reflect-pad MRD and strided
+    MPD weight-gradient variants at full size)."""
+    from oracle import ref_modules as O
+    from msmctts.networks.hifigan import UnivNetDiscriminator
+    cfg = _csmsc_cfg(256)
+    torch.manual_seed(4321)
     dd = UnivNetDiscriminator(_cfg(cfg["discriminator"]["mrd_config"]), _cfg(cfg["discriminator"]["mpd_config"]))
-    sd_d = {k: v.clone() for k, v in dd.state_dict().items()}
-    wav = (0.3 * torch.randn(4, 12000)).clamp(-1, 1)
+    sd_d = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in dd.state_dict().items()}
+    wav = (0.3 * torch.randn(32, 12000)).clamp(-1, 1)
     dd.to(DEV)
-    scores, feats = dd(wav.to(DEV))
-    with torch.no_grad():
-        rs, rf = O.discriminator(sd_d, "", wav, cfg["discriminator"])
+    wg = wav.to(DEV).requires_grad_(True)
+    wc = wav.clone().requires_grad_(True)
+    scores, feats = dd(wg)
+    rs, rf = O.discriminator(sd_d, "", wc, cfg["discriminator"])
     assert len(scores) == 10 and sum(len(f) for f in feats) == 55
     for i, (a, b) in enumerate(zip(scores, rs)):
         close(a, b, tol=2e-4, msg="score %d" % i)
     for i, (fa, fb) in enumerate(zip(feats, rf)):
         for j, (a, b) in enumerate(zip(fa, fb)):
             close(a, b, tol=2e-4, msg="feat %d.%d" % (i, j))
+
+    def scalar(sc, ft):
+        # LSGAN-like score term + feature-matching-like mean-abs term (the two ways the trainer consumes D)
+        return sum(((s - 1) ** 2).mean() for s in sc) + sum(f.abs().mean() for fl in ft for f in fl)
+    scalar(scores, feats).backward()
+    scalar(rs, rf).backward()
+    close(wg.grad, wc.grad, tol=1e-3, msg="grad wav", atol=2e-5 * float(wc.grad.abs().max()))
+    ref_grads = {k: v.grad for k, v in sd_d.items() if getattr(v, "grad", None) is not None}
+    assert len(ref_grads) > 150
+    check_grads(dd, ref_grads, tol=1e-3)

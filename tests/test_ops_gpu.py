@@ -426,6 +426,75 @@ def test_fused_adam_matches_torch(decoupled, wd):
         close(op.detach(), rp.detach(), tol=1e-5, msg="param after load_state_dict")
 
 
+def test_fused_adam_per_parameter_steps_and_fused_clip():
+    """(1) a parameter without a gradient during the first steps (the HiFiGAN decoder during the reference's 50k
+    warm-up steps) must start its bias correction at step 1 when it finally gets one -- torch keeps `step` per
+    parameter; (2) the global-norm clip folded into the update launches == clip_grad_norm_ + step."""
+    from msmctts.trainers.optimizers.fused import FusedAdam
+    dev = _dev()
+    gen = torch.Generator().manual_seed(11)
+    shapes = [(33,), (40000,), (128, 65), (5,)]
+    ref_p = [torch.randn(s, generator=gen).requires_grad_(True) for s in shapes]
+    our_p = [p.detach().clone().to(dev).requires_grad_(True) for p in ref_p]
+    kw = dict(lr=2e-4, betas=(0.8, 0.99), eps=1e-8, weight_decay=0.0)
+    ref = torch.optim.AdamW(ref_p, **kw)
+    ours = FusedAdam(our_p, decoupled=True, **kw)
+    late = {1, 3}                                   # these get their first gradient at step 4
+    for step in range(8):
+        for i, (rp, op) in enumerate(zip(ref_p, our_p)):
+            if i in late and step < 4:
+                rp.grad, op.grad = None, None
+                continue
+            g = torch.randn(rp.shape, generator=gen) * (0.5 + step)
+            rp.grad = g.clone()
+            op.grad = g.to(dev)
+        clip = 1.0 if step % 2 == 0 else None       # alternate clipped / unclipped steps
+        if clip is not None:
+            want_norm = torch.nn.utils.clip_grad_norm_([p for p in ref_p if p.grad is not None], clip)
+        ref.step()
+        ours.step(max_grad_norm=clip)
+        if clip is not None:
+            close(ours.last_grad_norm, want_norm, tol=1e-5, msg="grad norm step %d" % step)
+            for i, (rp, op) in enumerate(zip(ref_p, our_p)):
+                if rp.grad is not None:
+                    close(op.grad, rp.grad, tol=1e-5, msg="clipped grad %d" % i)
+    torch.cuda.synchronize()
+    for i, (rp, op) in enumerate(zip(ref_p, our_p)):
+        close(op.detach(), rp.detach(), tol=1e-5, msg="param %d" % i)
+    sd = ours.state_dict()
+    assert [float(sd["state"][i]["step"]) for i in range(4)] == [8.0, 4.0, 8.0, 4.0]
+    # round trip through a checkpoint keeps the per-parameter counters
+    ours2 = FusedAdam([p.detach().clone().requires_grad_(True) for p in our_p], decoupled=True, **kw)
+    ours2.load_state_dict(sd)
+    for op in ours2.param_groups[0]["params"]:
+        op.grad = torch.ones_like(op)
+    ours2.step()
+    assert [float(ours2.state_dict()["state"][i]["step"]) for i in range(4)] == [9.0, 5.0, 9.0, 5.0]
+
+
+def test_vq_search_nan_row_does_not_fault():
+    """a diverged batch (NaN / Inf row) must yield an in-range index (the reference's (-dist).max(1) returns 0 for
+    an all-NaN row) instead of reading far outside the codebook; the other rows are unaffected"""
+    from msmctts._b200 import functional as Fn
+    from oracle import vq as OV
+    dev = _dev()
+    for heads, K, n in ((4, 256, 960), (4, 64, 3840), (4, 100, 257), (4, 256, 20011)):
+        dim = 64
+        rng = np.random.default_rng(K + n)
+        z = rng.standard_normal((n, heads * dim)).astype(np.float32)
+        E = rng.standard_normal((heads, dim, K)).astype(np.float32)
+        z[5, 3] = np.nan
+        z[17, 70] = np.inf
+        _, _, _, idx = OV.search_c(z, E)
+        q, d, i = Fn.vq_quantize(torch.from_numpy(z).to(dev), torch.from_numpy(E).to(dev), heads, dim)
+        torch.cuda.synchronize()
+        i = i.cpu()
+        assert int(i.min()) >= 0 and int(i.max()) < K
+        keep = torch.ones(n, dtype=torch.bool)
+        keep[17] = False      # an Inf row mixes +inf and NaN distances: any in-range index is acceptable there
+        assert torch.equal(i[keep], torch.from_numpy(idx)[keep]), "indices (NaN row -> 0 like the reference)"
+
+
 def test_library_fails_loudly_without_cuda_tensor():
     from msmctts._b200 import functional as Fn
     from msmctts._b200.lib import MsmcError

@@ -1,31 +1,21 @@
-"""PENDING (not collected: the file name does not match test_*.py).  Validation of the experimental two-phase
-tensor-core VQ search (csrc/vq_umma.cu, MSMC_VQ_UMMA=1) against the C oracle -- run on a B200 first thing in round 2:
-
-    MSMC_VQ_UMMA=1 python -m pytest tests/pending/gpu_vq_umma.py -q -p no:cacheprovider
-
-Indices, quantised rows and the commitment term must equal the exhaustive search bit for bit, including exact ties
-(duplicated codewords: the lowest index wins) and rows that coincide with a codeword."""
-import os
-import sys
-
+"""Two-phase tensor-core VQ search (csrc/vq_umma.cu: phase 1 scores all codewords with 3xTF32 tcgen05 MMAs and keeps
+every candidate within a provable margin of the approximate minimum, phase 2 re-scores the candidates with the
+oracle's exact sequential-fma arithmetic) against the C oracle.  Indices, quantised rows and the commitment term must
+equal the exhaustive search bit for bit, including exact ties (duplicated codewords: the lowest index wins) and rows
+that coincide with a codeword."""
 import numpy as np
 import pytest
 import torch
-
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "msmc-tts_b200"))
 
 pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("heads,K,n", [(4, 256, 3840), (4, 256, 960), (4, 64, 3840), (4, 128, 777), (2, 64, 100),
                                        (8, 128, 77), (1, 256, 130), (4, 256, 20011)])
-def test_vq_umma_bit_exact_vs_c_oracle(heads, K, n):
-    assert os.environ.get("MSMC_VQ_UMMA") == "1", "run with MSMC_VQ_UMMA=1"
+def test_vq_umma_bit_exact_vs_c_oracle(heads, K, n, monkeypatch):
     from msmctts._b200 import functional as Fn
     from oracle import vq as OV
-    assert Fn.VQ_UMMA
+    monkeypatch.setattr(Fn, "VQ_UMMA", True)
     dev = torch.device("cuda:0")
     dim = 64
     rng = np.random.default_rng(heads * 1000 + K + n)
