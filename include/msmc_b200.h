@@ -83,6 +83,10 @@ int msmc_umma_tile_n(int32_t out_channels, int64_t rows);
 int64_t msmc_weight_image_elems(int32_t T, int32_t Cs, int32_t Cd, int32_t role, int32_t split, int32_t BN);
 int msmc_weight_image(const float* w_gemm, float* image, int32_t T, int32_t Cs, int32_t Cd, int32_t role,
                       int32_t split, int32_t BN, void* stream);
+/* every operand image of a sub-network in ONE launch.  jobs = DEVICE table of int64 words, 9 per job:
+ * w_gemm, image, T, Cs, Cd, BN, role, split, blk0 (blk0 = sum over the preceding jobs of ceil(elements / 1024) with
+ * elements = msmc_weight_image_elems(.., split = 0, ..)); total_blocks = that sum over all jobs */
+int msmc_weight_image_multi(const int64_t* jobs, int32_t n_jobs, int64_t total_blocks, void* stream);
 int msmc_conv_forward_umma(const msmc_conv_geom* g, const float* src, const float* src_aux, const float* wimg,
                            const float* bias, const float* residual, const float* dst_aux, float* dst,
                            int32_t split, int32_t BN, void* stream);
@@ -115,6 +119,11 @@ int msmc_conv_wgrad(const msmc_conv_geom* g, const float* src, const float* src_
  * the kernel emits the GEMM layout [tap][cs][cd] directly.  g == NULL: plain re-layout (un-normalised weights). */
 int msmc_weight_norm_fwd(const float* v, const float* g, float* w, float* inv_norm, int32_t O, int32_t I,
                          int32_t J, int64_t so, int64_t si, int64_t sj, void* stream);
+/* the same for EVERY weight of a sub-network in one launch (the reference re-parametrises each layer inside its own
+ * forward: ~270 tiny launches per train step).  jobs = DEVICE table of int64 words, 11 per job:
+ * v, g (0 = plain re-layout), w, inv_norm (0 = not wanted), so, si, sj, O, I, J, row0 (= sum of O over the
+ * preceding jobs); total_rows = sum of O over all jobs.  Bit-identical to msmc_weight_norm_fwd per job. */
+int msmc_weight_norm_fwd_multi(const int64_t* jobs, int32_t n_jobs, int64_t total_rows, void* stream);
 int msmc_weight_norm_bwd(const float* dw, int64_t so, int64_t si, int64_t sj, const float* v, const float* g,
                          const float* inv_norm, float* dv, float* dg, int32_t O, int32_t I, int32_t J,
                          void* stream);

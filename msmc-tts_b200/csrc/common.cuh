@@ -65,4 +65,9 @@ int num_sms();
 int launch_wgrad_reduce(const msmc_conv_geom& g, const float* workspace, int splits, float* dw, float* dbias,
                         void* stream);
 
+// persistent, warp-specialised tap-reuse convolution (conv_persist.cu); MSMC_ERR_UNSUPPORTED = shape does not fit
+int conv_reuse_persistent(const msmc_conv_geom& g, const float* src, const float* src_aux, const float* wimg,
+                          const float* bias, const float* residual, const float* dst_aux, float* dst,
+                          int tap_stride, int n_taps, int pad_rows, int split, int BN, void* stream);
+
 }  // namespace msmc

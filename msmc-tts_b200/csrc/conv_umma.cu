@@ -380,7 +380,10 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
     // instruction descriptor: D = F32 (1<<4), A = B = TF32 (2<<7, 2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)(UM_BM >> 4) << 24);
-    if ((tid & 31) == 0) {
+    // the whole warp walks the loop with warp-uniform values; one elected lane issues (predicated, straight-line:
+    // see umma_tf32_pred -- inside `if (lane == 0)` every MMA cost ~90 cycles of issue latency)
+    {
+      const uint32_t elected = elect_one();
       int s = 0;
       uint32_t ph = 0;
       const uint32_t a_desc0 = desc_lo_k(smem_u32(sA)), b_desc0 = desc_lo_k(smem_u32(sB));
@@ -396,17 +399,17 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
           const uint32_t acc = (ks > 0 || k > 0) ? 1u : 0u;
           if (SPLIT) {
             const uint32_t a_lo = a_hi + (A_PLANE >> 4), b_lo = b_hi + (B_PLANE >> 4);
-            umma_tf32_lo<DESC_HI_K>(tmem_base, a_lo, b_hi, IDESC, acc);   // small terms first
-            umma_tf32_lo<DESC_HI_K>(tmem_base, a_hi, b_lo, IDESC, 1u);
-            umma_tf32_lo<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, 1u);
+            umma_tf32_pred<DESC_HI_K>(tmem_base, a_lo, b_hi, IDESC, acc, elected);   // small terms first
+            umma_tf32_pred<DESC_HI_K>(tmem_base, a_hi, b_lo, IDESC, 1u, elected);
+            umma_tf32_pred<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, 1u, elected);
           } else {
-            umma_tf32_lo<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, acc);
+            umma_tf32_pred<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, acc, elected);
           }
         }
-        umma_commit(&empty_bar[s]);   // frees the stage when these MMAs have read it
+        umma_commit_pred(&empty_bar[s], elected);   // frees the stage when these MMAs have read it
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
-      if (n_k > 0) umma_commit(accum_bar);
+      if (n_k > 0) umma_commit_pred(accum_bar, elected);
     }
     __syncwarp();
   }
@@ -622,7 +625,8 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
     // ================================= MMA issuer =================================
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                ((uint32_t)(UM_BM >> 4) << 24);
-    if ((tid & 31) == 0) {
+    {
+      const uint32_t elected = elect_one();     // convergent, predicated issue (see umma_tf32_pred)
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const uint32_t a_desc0 = desc_lo_k(smem_u32(sA)), b_desc0 = desc_lo_k(smem_u32(sB));
@@ -642,20 +646,20 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
             const uint32_t acc = (kc > 0 || t > 0 || k > 0) ? 1u : 0u;
             if (SPLIT) {
               const uint32_t a_lo = a_hi + (A_PLANE >> 4), b_lo = b_hi + (B_PLANE >> 4);
-              umma_tf32_lo<DESC_HI_K>(tmem_base, a_lo, b_hi, IDESC, acc);
-              umma_tf32_lo<DESC_HI_K>(tmem_base, a_hi, b_lo, IDESC, 1u);
-              umma_tf32_lo<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, 1u);
+              umma_tf32_pred<DESC_HI_K>(tmem_base, a_lo, b_hi, IDESC, acc, elected);
+              umma_tf32_pred<DESC_HI_K>(tmem_base, a_hi, b_lo, IDESC, 1u, elected);
+              umma_tf32_pred<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, 1u, elected);
             } else {
-              umma_tf32_lo<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, acc);
+              umma_tf32_pred<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, acc, elected);
             }
           }
-          umma_commit(&eb[sb]);
+          umma_commit_pred(&eb[sb], elected);
           if (++sb == NBS) { sb = 0; pb ^= 1u; }
         }
-        umma_commit(&ea[sa]);
+        umma_commit_pred(&ea[sa], elected);
         if (++sa == NA) { sa = 0; pa ^= 1u; }
       }
-      umma_commit(accum_bar);
+      umma_commit_pred(accum_bar, elected);
     }
     __syncwarp();
   } else {
@@ -936,7 +940,8 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
     // ================================= MMA issuer =================================
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((1u << 15) | (1u << 16)) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
-    if ((tid & 31) == 0) {
+    {
+      const uint32_t elected = elect_one();     // convergent, predicated issue (see umma_tf32_pred)
       int s = 0;
       uint32_t ph = 0;
       const uint32_t a_desc0 = desc_lo_mn(smem_u32(sA));
@@ -957,18 +962,18 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
             const uint32_t acc = (ks > 0 || kg > 0) ? 1u : 0u;
             if (SPLIT) {
               const uint32_t a_lo = a_hi + (A_PLANE >> 4), b_lo = b_hi + (B_PLANE >> 4);
-              umma_tf32_lo<HI>(tmem_base, a_lo, b_hi, IDESC, acc);
-              umma_tf32_lo<HI>(tmem_base, a_hi, b_lo, IDESC, 1u);
-              umma_tf32_lo<HI>(tmem_base, a_hi, b_hi, IDESC, 1u);
+              umma_tf32_pred<HI>(tmem_base, a_lo, b_hi, IDESC, acc, elected);
+              umma_tf32_pred<HI>(tmem_base, a_hi, b_lo, IDESC, 1u, elected);
+              umma_tf32_pred<HI>(tmem_base, a_hi, b_hi, IDESC, 1u, elected);
             } else {
-              umma_tf32_lo<HI>(tmem_base, a_hi, b_hi, IDESC, acc);
+              umma_tf32_pred<HI>(tmem_base, a_hi, b_hi, IDESC, acc, elected);
             }
           }
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit_pred(&empty_bar[s], elected);
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
-      umma_commit(accum_bar);
+      umma_commit_pred(accum_bar, elected);
     }
     __syncwarp();
   }
@@ -1213,7 +1218,8 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_reuse_kernel(const 
     // ================================= MMA issuer =================================
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
-    if ((tid & 31) == 0) {
+    {
+      const uint32_t elected = elect_one();     // convergent, predicated issue (see umma_tf32_pred)
       int s = 0;
       uint32_t ph = 0;
       // A: the four M blocks are four taps -> LBO = d rows; B: 32-channel N blocks 4 KB apart
@@ -1236,18 +1242,18 @@ __global__ void __launch_bounds__(UMF_THREADS, 1) conv_wgrad_reuse_kernel(const 
             const uint32_t acc = (ks > 0 || kg > 0) ? 1u : 0u;
             if (SPLIT) {
               const uint32_t a_lo = a_hi + a_plane, b_lo = b_hi + (B_PLANE >> 4);
-              umma_tf32_lo<DESC_HI_MN>(td, a_lo, b_hi, IDESC, acc);
-              umma_tf32_lo<DESC_HI_MN>(td, a_hi, b_lo, IDESC, 1u);
-              umma_tf32_lo<DESC_HI_MN>(td, a_hi, b_hi, IDESC, 1u);
+              umma_tf32_pred<DESC_HI_MN>(td, a_lo, b_hi, IDESC, acc, elected);
+              umma_tf32_pred<DESC_HI_MN>(td, a_hi, b_lo, IDESC, 1u, elected);
+              umma_tf32_pred<DESC_HI_MN>(td, a_hi, b_hi, IDESC, 1u, elected);
             } else {
-              umma_tf32_lo<DESC_HI_MN>(td, a_hi, b_hi, IDESC, acc);
+              umma_tf32_pred<DESC_HI_MN>(td, a_hi, b_hi, IDESC, acc, elected);
             }
           }
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit_pred(&empty_bar[s], elected);
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
-      umma_commit(accum_bar);
+      umma_commit_pred(accum_bar, elected);
     }
     __syncwarp();
   }
@@ -1301,6 +1307,58 @@ __global__ void weight_image_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
+// Multi-tensor form of weight_image_kernel: every operand image a sub-network needs in ONE launch.  Job table
+// (device, int64 words, 9 per job): w, img, T, Cs, Cd, BN, role, split, blk0 where blk0 = sum over the preceding jobs
+// of ceil(elements / 1024); CTA b serves 1024 destination elements of its job (256 threads x 4).
+constexpr int IMG_JOB_WORDS = 9;
+__global__ void __launch_bounds__(256) weight_image_multi_kernel(const long long* __restrict__ jobs, int n_jobs) {
+  int lo = 0, hi = n_jobs - 1;
+  const long long blk = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[(size_t)mid * IMG_JOB_WORDS + 8] <= blk) lo = mid; else hi = mid - 1;
+  }
+  const long long* jb = jobs + (size_t)lo * IMG_JOB_WORDS;
+  const float* __restrict__ w = reinterpret_cast<const float*>(jb[0]);
+  float* __restrict__ img = reinterpret_cast<float*>(jb[1]);
+  const int T = (int)jb[2], Cs = (int)jb[3], Cd = (int)jb[4], BN = (int)jb[5], role = (int)jb[6], split = (int)jb[7];
+  const int Kdim = role ? Cd : Cs;
+  const int Ndim = role ? Cs : Cd;
+  const int KC = Kdim / 32;
+  const int NT = (Ndim + BN - 1) / BN;
+  const int64_t total = (int64_t)T * KC * NT * BN * 32;
+  const int64_t base = (blk - jb[8]) * 1024;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t e = base + q * 256 + threadIdx.x;
+    if (e >= total) break;
+    int64_t r = e;
+    const int j = (int)(r & 3); r >>= 2;
+    const int cphys = (int)(r & 7); r >>= 3;
+    const int nrow = (int)(r % BN); r /= BN;
+    const int nt = (int)(r % NT); r /= NT;
+    const int kc = (int)(r % KC);
+    const int tp = (int)(r / KC);
+    const int c = cphys ^ (nrow & 7);
+    const int k = kc * 32 + c * 4 + j;
+    const int n = nt * BN + nrow;
+    float val = 0.f;
+    if (n < Ndim) {
+      const int t = (role == 1) ? (T - 1 - tp) : tp;
+      const int cs = role ? n : k, cd = role ? k : n;
+      val = w[((int64_t)t * Cs + cs) * Cd + cd];
+    }
+    if (split) {
+      const int64_t tile = e / (BN * 32), within = e - tile * (BN * 32);
+      const float hi_v = __uint_as_float(__float_as_uint(val) & 0xFFFFE000u);
+      img[tile * (2 * BN * 32) + within] = hi_v;
+      img[tile * (2 * BN * 32) + BN * 32 + within] = val - hi_v;
+    } else {
+      img[e] = val;
+    }
+  }
+}
+
 }  // namespace
 
 // N tile.  Measured on B200 (profiles/r01_sweep_bn.txt): the tensor pipe retires a 128 x N x 8 TF32 MMA in roughly
@@ -1345,6 +1403,14 @@ extern "C" int msmc_weight_image(const float* w_gemm, float* image, int32_t T, i
   MSMC_REQUIRE(total > 0);
   const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)num_sms() * 8);
   weight_image_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_gemm, image, T, Cs, Cd, BN, role, split);
+  MSMC_CHECK_LAUNCH();
+  return MSMC_OK;
+}
+
+extern "C" int msmc_weight_image_multi(const int64_t* jobs, int32_t n_jobs, int64_t total_blocks, void* stream) {
+  MSMC_REQUIRE(jobs && n_jobs > 0 && total_blocks > 0 && total_blocks < ((int64_t)1 << 31));
+  weight_image_multi_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(jobs), n_jobs);
   MSMC_CHECK_LAUNCH();
   return MSMC_OK;
 }
@@ -1623,6 +1689,21 @@ extern "C" int msmc_conv_forward_umma_reuse(const msmc_conv_geom* gp, const floa
                (src_aux && g.ld_saux % 4 == 0 && (reinterpret_cast<uintptr_t>(src_aux) & 15) == 0));
   MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || dst_aux);
   MSMC_REQUIRE(BN == 32 || BN == 64 || BN == 128);
+  {
+    // persistent warp-specialised schedule (conv_persist.cu); MSMC_REUSE_PERSIST=0 keeps the one-tile-per-CTA kernel
+    // Measured on B200 (profiles/r02_bench_reuse_d.txt): the persistent schedule wins where one launch holds several
+    // rounds of long items (many position tiles x >= 7 taps: the 32/64-channel MRF convs, 50 vs 58 us and 64 vs 72 us
+    // at k = 11); short items (k = 3) and grids of about one wave are faster one tile per CTA, two CTAs per SM.
+    // MSMC_REUSE_PERSIST = 0 / 1 forces one or the other (read per call: the tests switch it).
+    const char* e_persist = getenv("MSMC_REUSE_PERSIST");
+    const int64_t tiles128 = (int64_t)g.B * ceil_div(g.Hd * g.Wd, UM_BM) * ceil_div(g.Cd, BN);
+    const bool want_persist = e_persist ? atoi(e_persist) != 0 : (a.n_taps >= 7 && tiles128 >= 3 * (int64_t)num_sms());
+    if (want_persist) {
+      const int rc = conv_reuse_persistent(g, src, src_aux, wimg, bias, residual, dst_aux, dst, a.tap_stride,
+                                           a.n_taps, a.pad_rows, split, BN, stream);
+      if (rc != MSMC_ERR_UNSUPPORTED) return rc;
+    }
+  }
   a.g = g; a.src = src; a.src_aux = src_aux; a.wimg = wimg; a.bias = bias; a.residual = residual;
   a.dst_aux = dst_aux; a.dst = dst;
   a.Ls = g.Hs * g.Ws; a.Ld = g.Hd * g.Wd;

@@ -77,6 +77,41 @@ __device__ __forceinline__ void umma_tf32_lo(uint32_t tmem_d, uint32_t a_lo32, u
       : "r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "n"(HI)
       : "memory");
 }
+// Same instruction issued from CONVERGENT code: every lane of the warp executes the asm with identical operands and
+// `elected` is non-zero in exactly one lane (elect_one).  Inside `if (lane == 0) { ... }` ptxas guards every
+// tcgen05.mma with its own ELECT / BRA.U.ANY loop (~90 cycles of issue latency per MMA, which -- not the tensor pipe --
+// paced every N <= 128 kernel of round 1); predicated straight-line code issues them back to back.
+template <uint32_t HI>
+__device__ __forceinline__ void umma_tf32_pred(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t elected) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "n"(HI), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t elected) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(elected)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");

@@ -66,9 +66,69 @@ def _weight_image(w, T, Cs, Cd, role, split, bn):
     if img is None:
         n = L.load().msmc_weight_image_elems(T, Cs, Cd, role, split, bn)
         img = torch.empty(n, dtype=torch.float32, device=w.device)
-        L.call("msmc_weight_image", L.ptr(w), L.ptr(img), T, Cs, Cd, role, split, bn)
+        if DEFERRED[0] is not None:
+            # prefetch_weights batches every image of the sub-network into one msmc_weight_image_multi launch
+            DEFERRED[0]["img"].append((w, img, T, Cs, Cd, bn, role, split, n // (2 if split else 1)))
+        else:
+            L.call("msmc_weight_image", L.ptr(w), L.ptr(img), T, Cs, Cd, role, split, bn)
         cache[key] = img
     return img
+
+
+# ---- deferred multi-tensor weight preparation (layers.prefetch_weights): job lists + pointer-table staging
+DEFERRED = [None]
+_prep_staging = {}
+
+
+def _job_table(key, words, device):
+    """int64 job table -> device through pinned staging (graph-capturable H2D copy).  Same discipline as the other
+    multi-tensor pointer tables: a table used inside a CUDA-graph capture gets a PRIVATE staging pair (taken from
+    spares allocated by an earlier eager call), because the captured copy re-reads the pinned buffer on every
+    replay; an eager call waits for its previous copy out of the pinned buffer before rewriting it."""
+    capturing = torch.cuda.is_current_stream_capturing()
+    n = len(words)
+    st = _prep_staging.get(key)
+    if st is None or st["n"] != n:
+        if capturing:
+            raise L.MsmcError("weight prefetch: run one eager step with this model before capturing a CUDA graph")
+        st = {"n": n, "pair": _staging(n, device), "spares": [_staging(n, device) for _ in range(3)],
+              "event": None, "graph_pairs": []}
+        _prep_staging[key] = st
+    if capturing:
+        if not st["spares"]:
+            raise L.MsmcError("weight prefetch: no private staging buffer left for another CUDA-graph capture")
+        host, table = st["spares"].pop()
+        st["graph_pairs"].append((host, table))
+    else:
+        if st["event"] is not None:
+            st["event"].synchronize()
+        host, table = st["pair"]
+    host.copy_(torch.tensor(words, dtype=torch.int64))
+    table.copy_(host, non_blocking=True)
+    if not capturing:
+        st["event"] = torch.cuda.Event()
+        st["event"].record()
+    return table
+
+
+def flush_deferred(jobs, key):
+    """launch the batched re-parametrisation and the batched operand images recorded in `jobs`"""
+    wn, img = jobs["wn"], jobs["img"]
+    if wn:
+        words, row0 = [], 0
+        for (v, g, w, inv, O, I, J, so, si, sj) in wn:
+            words += [v.data_ptr(), g.data_ptr() if g is not None else 0, w.data_ptr(),
+                      inv.data_ptr() if inv is not None else 0, so, si, sj, O, I, J, row0]
+            row0 += O
+        table = _job_table((key, "wn"), words, wn[0][0].device)
+        L.call("msmc_weight_norm_fwd_multi", L.ptr(table), len(wn), C.c_int64(row0))
+    if img:
+        words, blk0 = [], 0
+        for (w, im, T, Cs, Cd, bn, role, split, elems) in img:
+            words += [w.data_ptr(), im.data_ptr(), T, Cs, Cd, bn, role, split, blk0]
+            blk0 += (elems + 1023) // 1024
+        table = _job_table((key, "img"), words, img[0][0].device)
+        L.call("msmc_weight_image_multi", L.ptr(table), len(img), C.c_int64(blk0))
 
 
 def _umma_ok(src, ld_src, w, wstr_gemm, KH, KW, Cs, Cd_gemm, rows, saux, ld_saux):
@@ -448,8 +508,11 @@ class _PrepWeightFn(torch.autograd.Function):
         L.require_cuda(v, g)
         meta = {"flops": 0.0, "bytes": 8.0 * O * I * J, "shape": "O%d I%d J%d %s" % (O, I, J, "wn" if g is not None else "relayout")} \
             if L._profile is not None else None
-        L.call("msmc_weight_norm_fwd", L.ptr(v), L.ptr(g), L.ptr(w), L.ptr(inv), O, I, J,
-               C.c_int64(so), C.c_int64(si), C.c_int64(sj), meta=meta)
+        if DEFERRED[0] is not None:
+            DEFERRED[0]["wn"].append((v, g, w, inv, O, I, J, so, si, sj))     # one batched launch later
+        else:
+            L.call("msmc_weight_norm_fwd", L.ptr(v), L.ptr(g), L.ptr(w), L.ptr(inv), O, I, J,
+                   C.c_int64(so), C.c_int64(si), C.c_int64(sj), meta=meta)
         ctx.dims = (O, I, J, so, si, sj)
         ctx.has_g = g is not None
         ctx.save_for_backward(v, g, inv)

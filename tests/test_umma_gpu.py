@@ -152,3 +152,55 @@ def test_linear_umma(monkeypatch):
     close(xc.grad, xr.grad, 2e-5, "dx")
     close(Wc.grad, Wr.grad, 1e-4, "dW")
     close(bc.grad, br.grad, 1e-4, "db")
+
+
+PERSIST_SHAPES = [
+    # B, L, Ci, Co, K, dilation, residual : chosen so that the persistent kernel runs several rounds of work items
+    # per CTA, partial last tiles, several channel tiles and several 32-channel chunks
+    (4, 12000, 32, 32, 11, 5, True),      # 376 items at NACC=1 (2.5 rounds), reach 50
+    (3, 6000, 64, 64, 7, 3, True),        # KC=2
+    (5, 1200, 128, 128, 3, 1, False),     # KC=4, BN=128
+    (16, 240, 256, 512, 3, 1, False),     # FFN-like: 4 channel tiles, L < 256
+    (16, 60, 512, 256, 3, 1, False),      # short sequences (60 of 128 rows used)
+    (2, 1000, 96, 200, 5, 2, False),      # ragged channels (Cd not a multiple of the tile)
+]
+
+
+@pytest.mark.parametrize("nacc", [0, 1, 2, 4], ids=["auto", "nacc1", "nacc2", "nacc4"])
+@pytest.mark.parametrize("shape", PERSIST_SHAPES, ids=["B%d_L%d_C%d-%d_k%d_d%d" % s[:6] for s in PERSIST_SHAPES])
+def test_persistent_reuse_kernel_vs_one_tile_kernel_and_cpu(shape, nacc, monkeypatch):
+    """conv_reuse_persist_kernel (persistent grid, warp-specialised roles, NACC accumulators per weight pass,
+    double-buffered TMEM) against (1) the round-1 one-tile-per-CTA tap-reuse kernel: identical MMAs in identical
+    order per output element -> bit-identical results, and (2) torch fp32 on the CPU (2e-5 of the tensor max).
+    Forward and the stride-1 data gradient (same kernel, reversed-tap weight image) at every forced NACC."""
+    from msmctts._b200 import functional as Fn
+    monkeypatch.setattr(Fn, "CONV_MATH", "3xtf32")
+    B, Ln, Ci, Co, K, d, use_res = shape
+    gen = torch.Generator().manual_seed(Ln + Ci + K)
+    x = torch.randn(B, 1, Ln, Ci, generator=gen)
+    w = torch.randn(1, K, Ci, Co, generator=gen) / (Ci * K) ** 0.5
+    bias = torch.randn(Co, generator=gen) * 0.1
+    res = torch.randn(B, 1, Ln, Co, generator=gen) if use_res else None
+    wgt = torch.randn(B, 1, Ln, Co, generator=gen)
+    pad = (K * d - d) // 2
+    outs = []
+    for persist in ("1", "0"):
+        monkeypatch.setenv("MSMC_REUSE_PERSIST", persist)
+        if nacc:
+            monkeypatch.setenv("MSMC_PERSIST_NACC", str(nacc))
+        xc = x.to(DEV).requires_grad_(True)
+        y = Fn.conv_cl(xc, w.to(DEV), bias.to(DEV), res.to(DEV) if use_res else None, kernel=(1, K),
+                       dilation=(1, d), padding=(0, pad), pre_slope=0.1)
+        (y * wgt.to(DEV)).sum().backward()
+        torch.cuda.synchronize()
+        outs.append((y.detach(), xc.grad.detach()))
+    assert torch.equal(outs[0][0], outs[1][0]), "forward: persistent vs one-tile kernel must be bit-identical"
+    assert torch.equal(outs[0][1], outs[1][1]), "data gradient: persistent vs one-tile kernel must be bit-identical"
+    xr = x.clone().requires_grad_(True)
+    y_ref = F.conv1d(F.leaky_relu(xr[:, 0].transpose(1, 2), 0.1), w[0].permute(2, 1, 0).contiguous(), bias,
+                     padding=pad, dilation=d).transpose(1, 2).unsqueeze(1)
+    if use_res:
+        y_ref = y_ref + res
+    (y_ref * wgt).sum().backward()
+    close(outs[0][0], y_ref, 2e-5, "y vs cpu")
+    close(outs[0][1], xr.grad, 2e-5, "dx vs cpu")
