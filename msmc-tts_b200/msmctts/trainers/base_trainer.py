@@ -54,7 +54,8 @@ class BaseTrainer(object):
         lr_scheduler = build_lr_scheduler(self.config.lr_scheduler)
         iteration = self.attempt_load_checkpoint()
         logger = Logger(self.config.save_checkpoint_dir, "GPU_%d_" % self.rank if self.distributed else "",
-                        "GPU_%d.log" % self.rank if self.distributed else "train.log")
+                        "GPU_%d.log" % self.rank if self.distributed else "train.log",
+                        window=int(self.config.get("log_window", 100)), echo=bool(self.config.get("log_echo", False)))
         logger.info(json.dumps(self.config.to_dict(), indent=2, default=str))
         self.model.train()
         while True:

@@ -7,9 +7,10 @@ import torch
 
 
 class Logger(object):
-    def __init__(self, log_dir, prefix="", filename="train.log", window=100):
-        self.window, self.prefix = window, prefix
+    def __init__(self, log_dir, prefix="", filename="train.log", window=100, echo=False):
+        self.window, self.prefix, self.echo = window, prefix, echo
         self.sums, self.count = {}, 0
+        self.t_window = time.perf_counter()
         self.file = None
         if log_dir:
             os.makedirs(log_dir, exist_ok=True)
@@ -20,6 +21,8 @@ class Logger(object):
         if self.file:
             self.file.write(line + "\n")
             self.file.flush()
+        if self.echo:
+            print(self.prefix + line, flush=True)
 
     def log(self, iteration, log):
         for k, v in (log or {}).get("loss", {}).items():
@@ -27,6 +30,9 @@ class Logger(object):
             self.sums[k] = self.sums[k] + v if k in self.sums else v.clone()
         self.count += 1
         if self.count >= self.window:
-            self.info("iter %d: " % iteration + ", ".join(
-                "%s=%.5f" % (k, float(v) / self.count) for k, v in sorted(self.sums.items())))
-            self.sums, self.count = {}, 0
+            # float(v) is the one host sync of the window: the wall time per step below is honest device time
+            text = ", ".join("%s=%.5f" % (k, float(v) / self.count) for k, v in sorted(self.sums.items()))
+            now = time.perf_counter()
+            self.info("iter %d: %s | %.2f ms/step over the last %d steps" % (
+                iteration, text, (now - self.t_window) * 1e3 / self.count, self.count))
+            self.sums, self.count, self.t_window = {}, 0, now

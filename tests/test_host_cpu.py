@@ -143,6 +143,10 @@ g = task.autoencoder[0].weight.grad.clone()
 gathered = [torch.zeros_like(g) for _ in range(world)]
 dist.all_gather(gathered, g)
 assert torch.allclose(gathered[0], gathered[1]), "autoencoder grads were not averaged"
+# zero-copy hand-back: after finish() every .grad is a view into its bucket's reduced flat buffer
+ps = [p for p in task.autoencoder.parameters()]
+assert len({p.grad.untyped_storage().data_ptr() for p in ps}) == 1, "grads must alias one flat bucket"
+assert all(p.grad.shape == p.shape and p.grad.is_contiguous() for p in ps)
 gd = task.discriminator.weight.grad.clone()
 gathered = [torch.zeros_like(gd) for _ in range(world)]
 dist.all_gather(gathered, gd)
