@@ -57,6 +57,200 @@ def synth_batch(B, seed, device="cpu", pin=False):
     return batch
 
 
+AM_B, AM_L, AM_DUR = 32, 24, 10          # BASELINE.json configs[4]: B=32/GPU, 24 phonemes x 10 frames = T 240
+
+
+def load_am_cfg():
+    with open(os.path.join(ROOT, "tests", "golden", "csmsc_am_config.json")) as f:
+        return json.load(f)
+
+
+def synth_am_batch(B, seed, device="cpu", pin=False):
+    """text (B, 24, 3) ints in [1,100) x [1,10) x {0,1}, duration 10 frames per phoneme, mel as above"""
+    g = torch.Generator().manual_seed(seed)
+    text = torch.stack([torch.randint(1, 100, (B, AM_L), generator=g), torch.randint(1, 10, (B, AM_L), generator=g),
+                        torch.randint(0, 2, (B, AM_L), generator=g)], dim=-1)
+    T = AM_L * AM_DUR
+    batch = {"text": text, "text_length": torch.full((B,), AM_L, dtype=torch.int64),
+             "dur": torch.full((B, AM_L), AM_DUR, dtype=torch.int64),
+             "mel": (1.5 * torch.randn(B, T, N_MELS, generator=g)).clamp_(-4, 4),
+             "mel_length": torch.full((B,), T, dtype=torch.int64)}
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    if device != "cpu":
+        batch = {k: v.to(device) for k, v in batch.items()}
+    return batch
+
+
+def build_am_trainer(cfg, am, device, distributed, rank, world):
+    """PredictorTrainer on the CSMSC AM architecture with a frozen, random-init CSMSC autoencoder injected
+    (the reference loads it from a checkpoint, trainers/msmctts_trainer.py:288-295; there is none here)"""
+    from msmctts.networks.vqgantts import MSMCVQGAN
+    from msmctts.tasks.msmc_tts import MSMCTTS
+    from msmctts.trainers.msmctts_trainer import PredictorTrainer
+    from msmctts.utils.config import Config, ConfigItem
+    ycfg = {"id": "bench_am", "task": {"_name": "MSMCTTS", "_mode": "train_predictor",
+                                       "predictor": dict(am["predictor"], _name="MultiStagePredictor")},
+            "trainer": dict(am["trainer"]), "optimizer": am["optimizer"],
+            "dataset": {"_name": "SyntheticMelDataset", "samplerate": 24000, "feature": ["text", "dur", "mel"],
+                        "frameshift": [None, None, HOP]},
+            "dataloader": {"batch_size": AM_B * world, "num_workers": 0}}
+    config = Config(ycfg)
+    torch.manual_seed(config.seed)
+    task = MSMCTTS(config, mode="train")
+    kwargs = config.trainer.to_dict()
+    kwargs.pop("_name")
+    trainer = PredictorTrainer(config, task, num_gpus=world, rank=rank, **kwargs)
+    trainer.build_optimizer()
+    c = copy.deepcopy(cfg["autoencoder"])
+    torch.manual_seed(4321)
+    ae = MSMCVQGAN(c["in_dim"], c["n_model_size"], ConfigItem(c["encoder_config"]), ConfigItem(c["quantizer_config"]),
+                   ConfigItem(c["frame_decoder_config"]), ConfigItem(c["decoder_config"]), c["pred_mel"])
+    for p in ae.parameters():
+        p.requires_grad_(False)
+    trainer.build_autoencoder(ae.to(device))
+    task.train()
+    return trainer
+
+
+def am_workload_config(n):
+    return {"workload": "MSMC-VQ-GAN-AM PredictorTrainer.train_step: frozen CSMSC autoencoder analysis + "
+                        "MultiStagePredictor (FFT x 6 + 2 x FFT x 6, d_model 600, 114.8 M params) forward / backward, "
+                        "mse + triplet-sum embedding loss, duration loss, clip 10, Adam (BASELINE.json configs[4])",
+            "batch_per_gpu": AM_B, "global_batch": AM_B * n, "phonemes": AM_L, "mel_frames": AM_L * AM_DUR,
+            "n_mels": N_MELS, "codewords_per_head": K_CODEWORDS, "parallelism": "dp%d" % n,
+            "l2_policy": "per-step working set (114.8 M fp32 params + grads + Adam moments = 1.8 GB) exceeds the "
+                         "126 MB L2; no explicit flush"}
+
+
+def time_cpu_am_steps(cfg, am, steps, warmup):
+    from oracle.train_step import OraclePredictorTrainer
+    from msmctts.networks.acoustic_models import MultiStagePredictor
+    threads, ncpu = pick_cpu_threads(cfg)
+    torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    sd_ae, _ = init_state_dicts(cfg, 4321)
+    sd_p = MultiStagePredictor(**copy.deepcopy(am["predictor"])).state_dict()
+    tr = OraclePredictorTrainer(sd_p, sd_ae, am["predictor"], cfg["autoencoder"], am["trainer"],
+                                am["optimizer"]["_default"])
+    b = synth_am_batch(AM_B, 99)
+    args = (b["text"], b["text_length"], b["dur"], b["mel"], b["mel_length"])
+    for _ in range(warmup):
+        tr.step(*args)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(*args)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return AM_B * AM_L * AM_DUR / dt, dt, threads, ncpu
+
+
+def run_am(args, rank, world, local_rank):
+    """bench line of BASELINE.json configs[4] (`--config am`)"""
+    import torch.distributed as dist
+    from msmctts._b200 import lib as L
+    cfg, am = load_cfg(), load_am_cfg()
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = min(args.steps, 10), min(args.warmup, 2)
+        value, dt, threads, ncpu = time_cpu_am_steps(cfg, am, steps, warmup)
+        sample = "PredictorTrainer step at B=%d, %d timed steps after %d warm-up, %d torch threads of %d CPUs" % (
+            AM_B, steps, warmup, threads, ncpu)
+        print(json.dumps({"impl": "reference", "metric": "mel-frames/sec MSMC-VQ-GAN-AM predictor train step",
+                          "value": value, "unit": "mel-frames/s", "n_gpus": args.gpus, "steps": steps,
+                          "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": am_workload_config(args.gpus),
+                          "cpu_baseline": {"value": value, "unit": "mel-frames/s", "cores": threads, "kind": "port",
+                                           "sample": sample},
+                          "e2e": {"value": value, "unit": "mel-frames/s", "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}))
+        return
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    L.load()
+    distributed = world > 1
+    if distributed and not dist.is_initialized():
+        dist.init_process_group("nccl")
+    trainer = build_am_trainer(cfg, am, device, distributed, rank, world)
+    dev_batch = synth_am_batch(AM_B, 1000 + rank, device=device)
+    host_batches = [synth_am_batch(AM_B, 2000 + rank * 16 + i, pin=True) for i in range(4)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident(i):
+        return trainer.train_step(dev_batch, iteration=i)
+
+    def step_e2e(i):
+        hb = host_batches[i % len(host_batches)]
+        log = trainer.train_step({k: v.to(device, non_blocking=True) for k, v in hb.items()}, iteration=i)
+        return float(log["loss"]["total_loss"])
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if distributed:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for i in range(max(3, args.warmup)):
+        step_resident(i)
+    torch.cuda.synchronize()
+    l0 = L.launch_count
+    step_resident(99)
+    launches = L.launch_count - l0
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_step = timed(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    frames = AM_B * AM_L * AM_DUR * world
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+    # roofline: the predictor's dense contractions (409 GMAC forward, SURVEY 8a a19; x3 for fwd + dgrad + wgrad)
+    pk = peaks()
+    flops = 3 * 2 * 409e9 * world
+    ach = flops / (ms_step * 1e-3) / 1e12
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, threads, ncpu = time_cpu_am_steps(cfg, am, 2, 1)
+        cpu = {"value": v, "unit": "mel-frames/s", "cores": threads, "kind": "port",
+               "sample": "oracle port of the same PredictorTrainer step at the same batch (B=%d), 2 timed steps after "
+                         "1 warm-up (%.1f s/step); %d torch threads of the host's %d logical CPUs" % (
+                             AM_B, dt, threads, ncpu)}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "mel-frames/sec MSMC-VQ-GAN-AM predictor train step", "value": frames / (ms_step * 1e-3),
+            "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": am_workload_config(world), "clocks": clocks,
+            "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "mel-frames/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "cuda_graph": False,
+            "roofline": {"kernel": "whole step (conv / linear contractions of the predictor)", "bound": "tensor",
+                         "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"],
+                         "traffic": None, "peak_source": pk["source"],
+                         "note": "algorithmic flops = 3 x 2 x 409 GMAC (SURVEY 8a a19) over the device-timed step"},
+            "cpu_baseline": cpu}), flush=True)
+    if distributed:
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        dist.barrier()
+        dist.destroy_process_group()
+        os._exit(0)
+
+
 def family_traffic(entry):
     """DRAM bytes per launch of one C-ABI entry point's kernels, from the newest committed ncu capture of this same
     step (profiles/r*_family_traffic.json, written by profiles/family_traffic.py); None when there is none"""
@@ -537,10 +731,18 @@ def main():
     ap.add_argument("--reference-schedule", action="store_true",
                     help="replay the reference's launch schedule: 4 separate discriminator passes and discriminator "
                          "gradients computed (then discarded) in the generator step")
+    ap.add_argument("--config", default="gan", choices=["gan", "am"],
+                    help="gan: full GAN train step (the headline, BASELINE.json configs[1-3]); am: the multi-stage "
+                         "predictor train step of configs[4]")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.config == "am":
+        if args.impl != "reference" and not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl b200 needs a CUDA device (the hot path has no CPU fallback)")
+        run_am(args, rank, world, local_rank)
+        return
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) conv_reuse_persist_kernel(const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(te + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int KC = g.Cs / UM_BK;
+  const int KC = (g.Cs + UM_BK - 1) / UM_BK;      // ragged last chunk (Cs % 4 == 0) is zero-filled
   const int T = a.n_taps;
   const int NACC = a.nacc;
 
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(PR_THREADS, 1) conv_reuse_persist_kernel(const
         if (a.dry & 1) { vv[i] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
         const int r = c_rb * (32 * PR_RPB) + rsub + 32 * i;
         const int p = c_p0 + r;                             // source position inside this batch element
-        if (r < a.r_in && (unsigned)p < (unsigned)a.Ls) {
+        if (r < a.r_in && (unsigned)p < (unsigned)a.Ls && coff < g.Cs) {
           vv[i] = __ldg(reinterpret_cast<const float4*>(a.src + (c_pix0 + p) * g.ld_src + coff));
           if (NEED_AUX && need_aux)
             uu[i] = __ldg(reinterpret_cast<const float4*>(a.src_aux + (c_pix0 + p) * g.ld_saux + coff));

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
   if (m0 >= M) return;                       // (uniform per CTA; phases have slightly different row counts)
   const int n_tile = blockIdx.y;
   const int n_tiles = gridDim.y;
-  const int KC = g.Cs / UM_BK;
+  const int KC = (g.Cs + UM_BK - 1) / UM_BK;      // the last chunk may be ragged (Cs % 4 == 0): zero-filled
   int T = g.KH * g.KW;
   if (TRANSPOSED) {
     if (tid == 0) {
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
             ok = ok && (unsigned)hs < (unsigned)g.Hs && (unsigned)ws < (unsigned)g.Ws;
           }
         }
-        if (ok) {
+        if (ok && coff < g.Cs) {
           const int pix = pixb[i] + hs * g.Ws + ws;
           v[i] = __ldg(reinterpret_cast<const float4*>(a.src + (int64_t)pix * g.ld_src + coff));
           if (NEED_AUX && need_aux)
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
   const int b = blockIdx.x / a.tiles_per_batch;
   const int l0 = (blockIdx.x - b * a.tiles_per_batch) * UM_BM;
   const int n_tile = blockIdx.y, n_tiles = gridDim.y;
-  const int KC = g.Cs / UM_BK;
+  const int KC = (g.Cs + UM_BK - 1) / UM_BK;
   const int T = a.n_taps;
   const int r_in = UM_BM + (T - 1) * a.tap_stride;      // rows staged per chunk (<= RU_ROWS)
   constexpr int MMA_WARP = RU_PRODUCERS / 32;   // warp MMA_WARP + 1 streams the weight tiles
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
       for (int i = 0; i < 6; ++i) {
         const int r = rsub + 32 * i;
         const int p = l0 - a.pad_rows + r;               // source pixel inside this batch element
-        if (r < r_in && (unsigned)p < (unsigned)a.Ls) {
+        if (r < r_in && (unsigned)p < (unsigned)a.Ls && coff < g.Cs) {
           v[i] = __ldg(reinterpret_cast<const float4*>(a.src + (pix0 + p) * g.ld_src + coff));
           if (NEED_AUX && need_aux)
             u[i] = __ldg(reinterpret_cast<const float4*>(a.src_aux + (pix0 + p) * g.ld_saux + coff));
@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int KC = g.Cs / 32;
+  const int KC = (g.Cs + 31) / 32;                     // the last channel block may be ragged (Cs % 4 == 0)
   const int RB = g.KH * g.KW * KC;                     // row-blocks of dW
   const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
   const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
           int ws = wd * g.sw + kw * g.dw - g.pw;
           if (g.pad_reflect) { hs = reflect1(hs, g.Hs); ws = reflect1(ws, g.Ws); }
           else ok = ok && (unsigned)hs < (unsigned)g.Hs && (unsigned)ws < (unsigned)g.Ws;
-          if (ok) {
+          if (ok && cb * 32 + chunk * 4 < g.Cs) {
             const int64_t pix = ((int64_t)b * g.Hs + hs) * g.Ws + ws;
             v[i] = __ldg(reinterpret_cast<const float4*>(a.src + pix * g.ld_src + cb * 32 + chunk * 4));
             if (NEED_AUX && need_aux)
@@ -919,7 +919,7 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
     for (int c0 = cbeg; c0 < cbeg + CHALF; c0 += 16) {
       float acc[16];
       tmem_ld16(taddr + (uint32_t)c0, acc);
-      if (rb_ok) {
+      if (rb_ok && cb * 32 + lane < g.Cs) {
         if (n0 + c0 + 16 <= g.Cd && (g.Cd & 3) == 0) {
           // (the workspace is 256-byte aligned and every partial slab is a multiple of Cd floats long)
           float* out = part + krow * g.Cd + n0 + c0;
@@ -1272,7 +1272,7 @@ __global__ void weight_image_kernel(const float* __restrict__ w, float* __restri
                                     int BN, int role, int split) {
   const int Kdim = role ? Cd : Cs;   // reduction channels of this role
   const int Ndim = role ? Cs : Cd;
-  const int KC = Kdim / 32;
+  const int KC = (Kdim + 31) / 32;   // a ragged last chunk is zero-padded
   const int NT = (Ndim + BN - 1) / BN;
   const int64_t total = (int64_t)T * KC * NT * BN * 32;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -1289,7 +1289,7 @@ __global__ void weight_image_kernel(const float* __restrict__ w, float* __restri
     const int k = kc * 32 + c * 4 + j;
     const int n = nt * BN + nrow;
     float val = 0.f;
-    if (n < Ndim) {
+    if (n < Ndim && k < Kdim) {
       const int t = (role == 1) ? (T - 1 - tp) : tp;
       const int cs = role ? n : k, cd = role ? k : n;
       val = w[((int64_t)t * Cs + cs) * Cd + cd];
@@ -1324,7 +1324,7 @@ __global__ void __launch_bounds__(256) weight_image_multi_kernel(const long long
   const int T = (int)jb[2], Cs = (int)jb[3], Cd = (int)jb[4], BN = (int)jb[5], role = (int)jb[6], split = (int)jb[7];
   const int Kdim = role ? Cd : Cs;
   const int Ndim = role ? Cs : Cd;
-  const int KC = Kdim / 32;
+  const int KC = (Kdim + 31) / 32;
   const int NT = (Ndim + BN - 1) / BN;
   const int64_t total = (int64_t)T * KC * NT * BN * 32;
   const int64_t base = (blk - jb[8]) * 1024;
@@ -1343,7 +1343,7 @@ __global__ void __launch_bounds__(256) weight_image_multi_kernel(const long long
     const int k = kc * 32 + c * 4 + j;
     const int n = nt * BN + nrow;
     float val = 0.f;
-    if (n < Ndim) {
+    if (n < Ndim && k < Kdim) {
       const int t = (role == 1) ? (T - 1 - tp) : tp;
       const int cs = role ? n : k, cd = role ? k : n;
       val = w[((int64_t)t * Cs + cs) * Cd + cd];
@@ -1392,8 +1392,8 @@ extern "C" int msmc_umma_tile_n(int32_t out_channels, int64_t rows) { return umm
 extern "C" int64_t msmc_weight_image_elems(int32_t T, int32_t Cs, int32_t Cd, int32_t role, int32_t split,
                                            int32_t BN) {
   const int Kdim = role ? Cd : Cs, Ndim = role ? Cs : Cd;
-  if (Kdim % 32 != 0 || (BN != 32 && BN != 64 && BN != 128)) return -1;
-  return (int64_t)T * (Kdim / 32) * ceil_div(Ndim, BN) * BN * 32 * (split ? 2 : 1);
+  if (Kdim % 4 != 0 || (BN != 32 && BN != 64 && BN != 128)) return -1;
+  return (int64_t)T * ceil_div(Kdim, 32) * ceil_div(Ndim, BN) * BN * 32 * (split ? 2 : 1);
 }
 
 extern "C" int msmc_weight_image(const float* w_gemm, float* image, int32_t T, int32_t Cs, int32_t Cd, int32_t role,
@@ -1421,7 +1421,7 @@ extern "C" int msmc_conv_forward_umma(const msmc_conv_geom* gp, const float* src
   MSMC_REQUIRE(gp && src && wimg && dst);
   const msmc_conv_geom& g = *gp;
   MSMC_REQUIRE(!(g.transposed && g.pad_reflect));
-  MSMC_REQUIRE(g.Cs % UM_BK == 0 && g.ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  MSMC_REQUIRE(g.Cs % 4 == 0 && g.Cs >= UM_BK && g.ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
   MSMC_REQUIRE(!xf_needs_aux(g.src_xf) ||
                (src_aux && g.ld_saux % 4 == 0 && (reinterpret_cast<uintptr_t>(src_aux) & 15) == 0));
   MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || dst_aux);
@@ -1461,7 +1461,7 @@ extern "C" int msmc_conv_forward_umma(const msmc_conv_geom* gp, const float* src
   } while (0)
   // short reduction loops (the M-heavy, few-channel layers) are dominated by per-CTA prologue / epilogue latency:
   // a 2-stage ring halves the shared-memory footprint so two CTAs share an SM and overlap those phases
-  const int n_k_est = g.KH * g.KW * (g.Cs / UM_BK) / (g.transposed ? g.sh * g.sw : 1);
+  const int n_k_est = g.KH * g.KW * ceil_div(g.Cs, UM_BK) / (g.transposed ? g.sh * g.sw : 1);
   // measured on the full train step: two co-resident CTAs with 2-stage rings beat one CTA with a 4-stage ring for
   // every BN <= 64 shape (114.5 -> 111.5 ms/step), so "shallow" is the default; MSMC_UMMA_SHALLOW=2 restores the deep ring
   static const int shallow_mode = [] { const char* e = getenv("MSMC_UMMA_SHALLOW"); return e ? atoi(e) : 1; }();
@@ -1489,7 +1489,7 @@ namespace {
 int umma_wgrad_bn(int cd) { return cd <= 32 ? 32 : (cd <= 64 ? 64 : 128); }
 int umma_wgrad_splits(const msmc_conv_geom& g, int bn) {
   const int64_t M = (int64_t)g.B * g.Hd * g.Wd;
-  const int RB = g.KH * g.KW * (g.Cs / 32);
+  const int RB = g.KH * g.KW * ceil_div(g.Cs, 32);
   const int64_t tiles = (int64_t)ceil_div(RB, 4) * ceil_div(g.Cd, bn);
   // the producers are load-latency bound, so the BN <= 64 variants keep two CTAs per SM (2-stage rings); size the
   // position split so that all CTAs are co-resident in one wave (a third, nearly empty wave cost 33 % before)
@@ -1538,7 +1538,7 @@ bool wgrad_reuse_plan(const msmc_conv_geom& g, bool split, WgradReusePlan* p) {
 }  // namespace
 
 extern "C" int64_t msmc_conv_wgrad_umma_workspace(const msmc_conv_geom* gp) {
-  if (!gp || gp->Cs % 32 != 0) return -1;
+  if (!gp || gp->Cs % 4 != 0 || gp->Cs < 32) return -1;
   const msmc_conv_geom& g = *gp;
   {
     WgradReusePlan rp;
@@ -1554,7 +1554,8 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
                                     float* workspace, int64_t workspace_bytes, int32_t split, void* stream) {
   MSMC_REQUIRE(gp && src && gout && dw && workspace);
   const msmc_conv_geom& g = *gp;
-  MSMC_REQUIRE(!g.transposed && g.Cs % 32 == 0 && g.ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  MSMC_REQUIRE(!g.transposed && g.Cs % 4 == 0 && g.Cs >= 32 && g.ld_src % 4 == 0 &&
+               (reinterpret_cast<uintptr_t>(src) & 15) == 0);
   MSMC_REQUIRE(!xf_needs_aux(g.src_xf) ||
                (src_aux && g.ld_saux % 4 == 0 && (reinterpret_cast<uintptr_t>(src_aux) & 15) == 0));
   MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || gout_aux);
@@ -1620,7 +1621,7 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
            (!xf_needs_aux(g.dst_xf) || ((g.ld_daux % 4 == 0) && (reinterpret_cast<uintptr_t>(gout_aux) & 15) == 0));
   // every split must own at least one position so that each partial tile is written
   const int eff_splits = (int)ceil_div64(M, a.rows_per_split);
-  const int RB = g.KH * g.KW * (g.Cs / 32);
+  const int RB = g.KH * g.KW * ceil_div(g.Cs, 32);
   dim3 grid((unsigned)ceil_div(RB, 4), (unsigned)ceil_div(g.Cd, bn), (unsigned)eff_splits);
   cudaStream_t st = (cudaStream_t)stream;
   const int xfc = g.src_xf == MSMC_XF_NONE ? XFC_NONE
@@ -1673,7 +1674,7 @@ bool reuse_eligible(const msmc_conv_geom& g, int* tap_stride, int* n_taps, int* 
 
 extern "C" int msmc_conv_reuse_eligible(const msmc_conv_geom* gp) {
   int a, b, c;
-  return gp && gp->Cs % UM_BK == 0 && reuse_eligible(*gp, &a, &b, &c) ? 1 : 0;
+  return gp && gp->Cs % 4 == 0 && gp->Cs >= UM_BK && reuse_eligible(*gp, &a, &b, &c) ? 1 : 0;
 }
 
 extern "C" int msmc_conv_forward_umma_reuse(const msmc_conv_geom* gp, const float* src, const float* src_aux,
@@ -1684,7 +1685,7 @@ extern "C" int msmc_conv_forward_umma_reuse(const msmc_conv_geom* gp, const floa
   const msmc_conv_geom& g = *gp;
   ReuseArgs a;
   MSMC_REQUIRE(reuse_eligible(g, &a.tap_stride, &a.n_taps, &a.pad_rows));
-  MSMC_REQUIRE(g.Cs % UM_BK == 0 && g.ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  MSMC_REQUIRE(g.Cs % 4 == 0 && g.Cs >= UM_BK && g.ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
   MSMC_REQUIRE(!xf_needs_aux(g.src_xf) ||
                (src_aux && g.ld_saux % 4 == 0 && (reinterpret_cast<uintptr_t>(src_aux) & 15) == 0));
   MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || dst_aux);

@@ -132,7 +132,7 @@ def flush_deferred(jobs, key):
 
 
 def _umma_ok(src, ld_src, w, wstr_gemm, KH, KW, Cs, Cd_gemm, rows, saux, ld_saux):
-    if CONV_MATH == "fp32" or Cs % 32 != 0 or rows < UMMA_MIN_ROWS:
+    if CONV_MATH == "fp32" or Cs % 4 != 0 or Cs < 32 or rows < UMMA_MIN_ROWS:      # a ragged last 32-channel chunk is fine
         return False
     if not w.is_contiguous() or w.numel() != KH * KW * wstr_gemm[0] * wstr_gemm[1]:
         return False
@@ -219,7 +219,7 @@ def _launch_wgrad(src, gout, dw, wstr, dbias, KH, KW, sh, sw, dh, dw_, ph, pw, r
         meta = {"flops": 2.0 * B * Hd * Wd * KH * KW * Cs * Cd,
                 "bytes": 4.0 * (src.numel() + gout.numel() + KH * KW * Cs * Cd),
                 "shape": "wgrad B%d %dx%d C%d->%d k%dx%d" % (B, Hs, Ws, Cs, Cd, KH, KW)}
-    use_umma = (CONV_MATH != "fp32" and Cs % 32 == 0 and ld_src % 4 == 0 and src.data_ptr() % 16 == 0
+    use_umma = (CONV_MATH != "fp32" and Cs % 4 == 0 and Cs >= 32 and ld_src % 4 == 0 and src.data_ptr() % 16 == 0
                 and B * Hd * Wd >= UMMA_MIN_ROWS
                 and (saux is None or (g.ld_saux % 4 == 0 and saux.data_ptr() % 16 == 0)))
     if use_umma:
@@ -430,7 +430,7 @@ def linear_cl(x, weight, bias=None, residual=None, post="none", pre_slope=None, 
     lead = x.shape[:-1]
     x4 = x.reshape(-1, 1, 1, Ci)
     r4 = residual.reshape(-1, 1, 1, Co) if residual is not None else None
-    umma = CONV_MATH != "fp32" and Ci % 32 == 0 and x4.shape[0] >= UMMA_MIN_ROWS and weight.requires_grad
+    umma = CONV_MATH != "fp32" and Ci % 4 == 0 and Ci >= 32 and x4.shape[0] >= UMMA_MIN_ROWS and weight.requires_grad
     if owner is not None:
         owner.__dict__["_msmc_lin_umma"] = bool(umma)
     if umma:

@@ -156,7 +156,18 @@ class LengthRegulator(nn.Module):
         return out, pos, torch.round(duration).long()
 
     def get_output(self, x, duration, alpha):
-        reps = torch.round(duration.float() * alpha).long()
-        outs = [torch.repeat_interleave(x[i], reps[i], dim=0) for i in range(x.size(0))]
-        pos = [torch.arange(1, o.shape[0] + 1, device=x.device) for o in outs]
-        return pad_sequence(outs, batch_first=True), pad_sequence(pos, batch_first=True)
+        """x (B, L, C) expanded by per-token repeat counts -> (B, T, C), zero padded; positions 1..len (0 = pad).
+        The reference loops over the batch (repeat_interleave + pad_sequence per sample, transformer.py:470-489);
+        here one searchsorted + gather serves the whole batch.  The output length is data dependent, so ONE host
+        read of max(total) remains (the reference has B of them)."""
+        B, Ln, Cn = x.shape
+        reps = torch.round(duration.float() * alpha).long().clamp_min(0)
+        csum = reps.cumsum(1)
+        total = csum[:, -1]
+        T = int(total.max())
+        t = torch.arange(T, device=x.device).unsqueeze(0).expand(B, T)
+        idx = torch.searchsorted(csum, t.contiguous(), right=True).clamp_max(Ln - 1)
+        valid = t < total.unsqueeze(1)
+        out = torch.gather(x, 1, idx.unsqueeze(-1).expand(-1, -1, Cn)) * valid.unsqueeze(-1).to(x.dtype)
+        pos = torch.where(valid, t + 1, torch.zeros_like(t))
+        return out, pos

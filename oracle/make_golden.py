@@ -332,6 +332,21 @@ def gen_keys():
         out["discriminator_params"] / 1e6))
 
 
+def gen_am_config():
+    """BASELINE.json configs[4]: the yaml blocks of examples/csmsc/configs/msmc_vq_gan_am.yaml (predictor, trainer,
+    optimizer) for tests and bench.py --config am, plus the predictor's state_dict names / shapes."""
+    C = R.ref("msmctts.utils.config")
+    cfg = C.Config(os.path.join(R.REF_ROOT, "examples/csmsc/configs/msmc_vq_gan_am.yaml"))
+    P = R.ref("msmctts.networks.acoustic_models.multi_stage_predictor")
+    p_cfg = {k: v for k, v in cfg.task.predictor.to_dict().items() if not k.startswith("_")}
+    m = P.MultiStagePredictor(**{k: v for k, v in cfg.task.predictor.items() if not k.startswith("_")})
+    with open(os.path.join(OUT, "csmsc_am_config.json"), "w") as f:
+        json.dump(dict(predictor=p_cfg, trainer=cfg.trainer.to_dict(), optimizer=cfg.optimizer.to_dict(),
+                       predictor_keys={k: list(v.shape) for k, v in m.state_dict().items()},
+                       predictor_params=sum(p.numel() for p in m.parameters())), f, indent=1)
+    print("csmsc am: %d tensors %.2fM params" % (len(m.state_dict()), sum(p.numel() for p in m.parameters()) / 1e6))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     R.install()
@@ -344,3 +359,4 @@ if __name__ == "__main__":
     gen_predictor()
     gen_train_step()
     gen_keys()
+    gen_am_config()

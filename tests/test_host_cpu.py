@@ -189,7 +189,8 @@ def test_tile_policy_and_workspace_queries_run_without_a_gpu():
     assert lib.msmc_umma_tile_n(1, 12000) == 32
     # image size: T taps x (K/32) chunks x n-tiles x BN rows x 32 floats x (hi, lo planes)
     assert lib.msmc_weight_image_elems(3, 256, 1024, 0, 1, 128) == 3 * 8 * 8 * 128 * 32 * 2
-    assert lib.msmc_weight_image_elems(3, 100, 64, 0, 1, 64) == -1        # K not a multiple of 32
+    assert lib.msmc_weight_image_elems(3, 100, 64, 0, 1, 64) == 3 * 4 * 1 * 64 * 32 * 2   # ragged K: 4 chunks, padded
+    assert lib.msmc_weight_image_elems(3, 102, 64, 0, 1, 64) == -1        # K must be a multiple of 4 (16-byte rows)
     assert lib.msmc_adam_chunk_elems() > 0 and lib.msmc_l1_chunk_elems() > 0
 
 

@@ -20,7 +20,7 @@ def _no_dropout(model):
             mod.attn_dropout = 0.0
         if isinstance(mod, torch.nn.Dropout):
             mod.p = 0.0
-        if mod.__class__.__name__ == "MultiStageQuantizer":
+        if mod.__class__.__name__ in ("MultiStageQuantizer", "DurationPredictor"):
             mod.dropout = 0.0
 
 
@@ -177,3 +177,54 @@ def test_cuda_graph_replay_matches_eager_steps():
                 step, k, a[k], b[k])
     worst = max(float((x - y).abs().max()) for x, y in zip(*params))
     assert worst <= 1e-4, "parameters after 6 steps differ by %.3e" % worst
+
+
+def test_predictor_train_step_vs_oracle():
+    """BASELINE.json configs[4] at its real architecture (CSMSC AM yaml: d_model 600, FFT x 6 encoder + 2 x FFT x 6
+    decoders, 114.8 M parameters; frozen CSMSC autoencoder, K=256; 24 phonemes x 10 frames = T 240) on a B=4 slice:
+    PredictorTrainer.train_step (reference trainers/msmctts_trainer.py:237-286) vs the CPU oracle port from the same
+    state -- every logged loss of two consecutive steps (mse + triplet-sum embedding losses, duration loss, gradient
+    norm) and every parameter after the two clipped Adam updates."""
+    import bench
+    from oracle.train_step import OraclePredictorTrainer
+    cfg, am = bench.load_cfg(), bench.load_am_cfg()
+    dev = torch.device("cuda:0")
+    trainer = bench.build_am_trainer(cfg, am, dev, False, 0, 1)
+    _no_dropout(trainer.model)
+    sd_p = {k: v.detach().cpu().clone() for k, v in trainer.model.predictor.state_dict().items()}
+    sd_ae = {k: v.detach().cpu().clone() for k, v in trainer.autoencoder.state_dict().items()}
+    oracle = OraclePredictorTrainer(sd_p, sd_ae, am["predictor"], cfg["autoencoder"], am["trainer"],
+                                    am["optimizer"]["_default"])
+    B = 4
+    batch = bench.synth_am_batch(B, 21)
+    batch["text_length"] = torch.tensor([24, 24, 20, 17])
+    dur = batch["dur"].clone()
+    dur[0, :4] = torch.tensor([12, 8, 11, 9])                     # uneven durations, same total
+    for b, n in enumerate(batch["text_length"].tolist()):          # padded phonemes: id 0, duration 0
+        batch["text"][b, n:] = 0
+        dur[b, n:] = 0
+    batch["dur"] = dur
+    batch["mel_length"] = dur.sum(1)
+    keys = ("total_loss", "embed_loss_mse_0", "embed_loss_triple_sum_0", "embed_loss_mse_1", "embed_loss_triple_sum_1",
+            "dur_loss", "grad_norm")
+    for step in range(2):
+        log = trainer.train_step({k: v.to(dev) for k, v in batch.items()}, iteration=step)["loss"]
+        ref = oracle.step(batch["text"], batch["text_length"], batch["dur"], batch["mel"], batch["mel_length"])
+        bad = []
+        for k in keys:
+            a, b = float(log[k]), ref[k]
+            tol = 2e-3 if step == 0 else 2e-2
+            if not abs(a - b) <= tol * max(abs(b), 1e-3):
+                bad.append("step %d %s: %.6f vs %.6f" % (step, k, a, b))
+        assert not bad, "; ".join(bad)
+    lr = am["optimizer"]["_default"]["learning_rate"]
+    sd_gpu = trainer.model.predictor.state_dict()
+    n_checked = n_tight = 0
+    for k, v in oracle.sd_p.items():
+        if not v.is_floating_point():
+            continue
+        err = (sd_gpu[k].detach().cpu() - v.detach()).abs()
+        assert float(err.max()) <= 2.2 * 2 * lr, "predictor.%s differs by %.3e" % (k, float(err.max()))
+        n_tight += int((err <= 0.1 * lr).sum())
+        n_checked += err.numel()
+    assert n_tight >= 0.98 * n_checked, "only %.2f %% of the weights within 0.1 lr" % (100.0 * n_tight / n_checked)

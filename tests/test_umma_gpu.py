@@ -35,6 +35,13 @@ CASES = [
     ("k3 d1 L=1000 Cs32 (3 tiles/batch + tail)", 3, 1, 1000, 32, 48, 1, 3, (1, 1), (1, 1), (0, 1), False, None, "none", False),
     ("mrd 3x3 reflect s2 Cs32", 2, 40, 30, 32, 64, 3, 3, (2, 2), (1, 1), (1, 1), True, None, "lrelu", False),
     ("mrd 3x3 reflect s1 Cs64", 2, 21, 18, 64, 32, 3, 3, (1, 1), (1, 1), (1, 1), True, None, "lrelu", False),
+    # channel counts that are not multiples of 32 (the AM's d_model = 600, 1456-wide decoder input): the last
+    # 32-channel chunk of the reduction is ragged and zero-filled in the operand tiles / weight images
+    ("AM ffn1 Cs600 Cd1536 k3", 2, 1, 240, 600, 1536, 1, 3, (1, 1), (1, 1), (0, 1), False, None, "relu", False),
+    ("AM ffn2 Cs1536 Cd600 k3", 2, 1, 240, 1536, 600, 1, 3, (1, 1), (1, 1), (0, 1), False, None, "none", False),
+    ("AM downsampler Cs600 k9", 2, 1, 300, 600, 600, 1, 9, (1, 1), (1, 1), (0, 4), False, None, "none", False),
+    ("AM linear 1456->600", 1, 1, 480, 1456, 600, 1, 1, (1, 1), (1, 1), (0, 0), False, None, "none", False),
+    ("ragged Cs40 strided 2-D", 2, 30, 20, 40, 48, 3, 3, (2, 1), (1, 1), (1, 1), False, 0.2, "none", False),
 ]
 
 
@@ -98,7 +105,12 @@ def _run_case(case, tol, cmp=None):
 def test_conv_umma_3xtf32(case, monkeypatch):
     from msmctts._b200 import functional as Fn
     monkeypatch.setattr(Fn, "CONV_MATH", "3xtf32")
-    names = _run_case(case, 2e-5)
+    # 2e-5 of the tensor max up to reductions of ~1.5k terms (the GAN step's longest is 3 x 1024).  The hi / lo split
+    # TRUNCATES (hi = top 19 bits, the tensor core truncates lo to TF32 again), so every partial product carries a
+    # relative error of ~2^-22 with the SIGN OF THE PRODUCT: it does not average out, the bound grows with the
+    # reduction length (the AM's longest reductions are 9 x 600 and 3 x 1536 terms)
+    k_red = max(case[4], case[5]) * case[6] * case[7]
+    names = _run_case(case, 2e-5 * max(1.0, k_red / 1536.0))
     stride = case[8]
     if stride == (1, 1) and not case[11] and case[5] % 32 == 0:
         assert names.count("msmc_conv_forward_umma") == 2, "forward and stride-1 data gradient both on tensor cores"
