@@ -30,6 +30,16 @@ def _prepped(mod, v, g, transposed=False, swap_taps=False):
     every consumer stream waits on it."""
     scope = Fn.PREP_SCOPE[0]
     if scope == 0:       # sharing is only safe inside a trainer step (nobody edits .data behind autograd's back there)
+        if not torch.is_grad_enabled():
+            # inference (no autograd graph): the re-parametrised GEMM-layout weight and the tensor-core operand images
+            # hanging off it are baked ONCE per parameter version (in-place updates bump `_version`), not per call
+            key = (v._version, -1 if g is None else g._version, v.data_ptr(), transposed, swap_taps)
+            hit = mod.__dict__.get("_msmc_infer_prep")
+            if hit is not None and hit[0] == key:
+                return hit[1]
+            w = Fn.prep_conv_weight(v.transpose(2, 3) if swap_taps else v, g, transposed=transposed)
+            mod.__dict__["_msmc_infer_prep"] = (key, w)
+            return w
         return Fn.prep_conv_weight(v.transpose(2, 3) if swap_taps else v, g, transposed=transposed)
     grad = torch.is_grad_enabled() and (v.requires_grad or (g is not None and g.requires_grad))
     key = (scope, v._version, -1 if g is None else g._version, grad, v.data_ptr())
@@ -150,6 +160,21 @@ class Conv1d(nn.Module):
         return y.squeeze(1)
 
 
+def _fold_weight_norm(mod):
+    """torch.nn.utils.remove_weight_norm semantics (reference hifigan/generator.py:57-64, common.py:43-51): replace
+    the (weight_g, weight_v) pair by the plain parameter `weight` = g * v / ||v|| (norm over all dims but 0)."""
+    if not hasattr(mod, "weight_v"):
+        raise ValueError("weight_norm of '%s' not found" % mod.__class__.__name__)
+    with torch.no_grad():
+        v, g = mod.weight_v, mod.weight_g
+        w = v * (g / v.norm(2, dim=tuple(range(1, v.dim())), keepdim=True))
+    del mod.weight_g
+    del mod.weight_v
+    mod.weight = nn.Parameter(w)
+    mod.__dict__.pop("_msmc_prep", None)
+    mod.__dict__.pop("_msmc_infer_prep", None)
+
+
 class WNConv1d(Conv1d):
     """weight_norm(nn.Conv1d): parameters `bias`, `weight_g` (Co,1,1), `weight_v` (Co,Ci,K) in that order."""
 
@@ -161,7 +186,12 @@ class WNConv1d(Conv1d):
         self.weight_v = nn.Parameter(v)
 
     def gemm_weight(self):
-        return self.weight_v, self.weight_g
+        if hasattr(self, "weight_v"):
+            return self.weight_v, self.weight_g
+        return self.weight, None                    # after remove_weight_norm()
+
+    def remove_weight_norm(self):
+        _fold_weight_norm(self)
 
 
 class WNConvTranspose1d(nn.Module):
@@ -176,11 +206,17 @@ class WNConvTranspose1d(nn.Module):
         self.weight_g = nn.Parameter(v.norm(2, dim=(1, 2), keepdim=True))
         self.weight_v = nn.Parameter(v)
 
+    def _vg(self):
+        return (self.weight_v, self.weight_g) if hasattr(self, "weight_v") else (self.weight, None)
+
+    def remove_weight_norm(self):
+        _fold_weight_norm(self)
+
     def _prep_spec(self):
-        return (self.weight_v, self.weight_g, True)
+        return self._vg() + (True,)
 
     def forward(self, x, pre_slope=None):
-        w = _prepped(self, self.weight_v, self.weight_g, transposed=True)
+        w = _prepped(self, *self._vg(), transposed=True)
         y = Fn.conv_cl(x.unsqueeze(1), w, self.bias, kernel=(1, self.kernel_size), stride=(1, self.stride),
                        padding=(0, self.padding), transposed=True, pre_slope=pre_slope)
         return y.squeeze(1)
@@ -201,18 +237,24 @@ class WNConv2d(nn.Module):
         self.weight_g = nn.Parameter(v.norm(2, dim=(1, 2, 3), keepdim=True))
         self.weight_v = nn.Parameter(v)
 
+    def _vg(self):
+        return (self.weight_v, self.weight_g) if hasattr(self, "weight_v") else (self.weight, None)
+
+    def remove_weight_norm(self):
+        _fold_weight_norm(self)
+
     def _prep_spec(self):
-        return (self.weight_v, self.weight_g, False, self.swap_hw)
+        return self._vg() + (False, self.swap_hw)
 
     def forward(self, x, pre_slope=None, post="none"):
         KH, KW = self.kernel_size
         if not self.swap_hw:
-            w = _prepped(self, self.weight_v, self.weight_g)   # [kh][kw][ci][co]
+            w = _prepped(self, *self._vg())   # [kh][kw][ci][co]
             return Fn.conv_cl(x, w, self.bias, kernel=(KH, KW), stride=self.stride, padding=self.padding,
                               reflect=self.reflect, pre_slope=pre_slope, post=post)
         # exchanged spatial axes: transpose the taps, then the standard contiguous GEMM layout [kw][kh][ci][co]
         # (the weight norm runs over (ci, kh, kw), so it is unaffected by the permutation)
-        w = _prepped(self, self.weight_v, self.weight_g, swap_taps=True)
+        w = _prepped(self, *self._vg(), swap_taps=True)
         return Fn.conv_cl(x, w, self.bias, kernel=(KW, KH), stride=self.stride[::-1], padding=self.padding[::-1],
                           reflect=self.reflect, pre_slope=pre_slope, post=post)
 

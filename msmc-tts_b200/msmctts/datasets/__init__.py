@@ -1,9 +1,14 @@
-"""Data path.  The reference's file-backed datasets (datasets/, utils.py:20-108) are out of the hot-path scope
-(SURVEY 2); this backend ships the synthetic batch source BASELINE.md section 5 defines, with pinned host memory so
-the H2D copy is asynchronous.  `_name: SyntheticMelDataset` in the yaml selects it."""
+"""Data path (reference datasets/__init__.py:9-34).  `_name` in the yaml `dataset` block selects the class:
+`MelDataset` / `TTSDataset` are the reference's file-backed datasets (own implementation, file_dataset.py),
+`SyntheticMelDataset` is the synthetic batch source BASELINE.md section 5 defines.  Unlike the reference the loader
+pins its batches (asynchronous H2D) and keeps its workers alive between epochs; `DevicePrefetcher` overlaps the copy of
+batch i+1 with step i."""
 import torch
 from torch.utils.data import DataLoader, Dataset
 from torch.utils.data.distributed import DistributedSampler
+
+from .file_dataset import FileDataset, MelDataset, TTSDataset
+from .prefetch import DevicePrefetcher
 
 
 class SyntheticMelDataset(Dataset):
@@ -14,7 +19,7 @@ class SyntheticMelDataset(Dataset):
         # examples/csmsc/configs/msmc_vq_gan.yaml): the mel entry is the hop
         if isinstance(frameshift, (list, tuple)):
             names = list(feature) if feature is not None else []
-            frameshift = frameshift[names.index("mel")] if "mel" in names else max(frameshift)
+            frameshift = frameshift[names.index("mel")] if "mel" in names else max(s for s in frameshift if s)
         self.n_items, self.n_frames, self.n_mels, self.seed = n_items, n_frames, n_mels, seed
         self.frameshift = int(frameshift)
 
@@ -29,15 +34,23 @@ class SyntheticMelDataset(Dataset):
                 "wav_length": torch.tensor(self.n_frames * self.frameshift)}
 
 
-def build_dataloader(dataset_config, dataloader_config, distributed=False):
+DATASETS = {"SyntheticMelDataset": SyntheticMelDataset, "MelDataset": MelDataset, "TTSDataset": TTSDataset}
+
+
+def build_dataset(dataset_config):
     name = dataset_config.get("_name", "SyntheticMelDataset")
-    if name != "SyntheticMelDataset":
-        raise NotImplementedError(
-            "dataset %s: file-backed datasets are outside this backend's scope; use the reference's "
-            "msmctts.datasets for real data, or _name: SyntheticMelDataset" % name)
+    if name not in DATASETS:
+        raise ValueError("unknown dataset %s (have: %s)" % (name, ", ".join(sorted(DATASETS))))
     kwargs = {k: v for k, v in dataset_config.items() if not k.startswith("_")}
-    ds = SyntheticMelDataset(**kwargs)
+    return DATASETS[name](**kwargs)
+
+
+def build_dataloader(dataset_config, dataloader_config, distributed=False):
+    ds = build_dataset(dataset_config)
     sampler = DistributedSampler(ds) if distributed else None
+    workers = int(dataloader_config.get("num_workers", 0))
+    collate = getattr(ds, "collate_fn", None)
     loader = DataLoader(ds, batch_size=dataloader_config.batch_size, shuffle=sampler is None, sampler=sampler,
-                        num_workers=dataloader_config.get("num_workers", 0), pin_memory=True, drop_last=True)
+                        num_workers=workers, collate_fn=collate, pin_memory=torch.cuda.is_available(), drop_last=True,
+                        persistent_workers=workers > 0, prefetch_factor=2 if workers > 0 else None)
     return ds, sampler, loader

@@ -29,6 +29,10 @@ class ResBlock1(nn.Module):
             x = c2(xt, pre_slope=LRELU_SLOPE, residual=x)
         return x
 
+    def remove_weight_norm(self):
+        for layer in list(self.convs1) + list(self.convs2):
+            layer.remove_weight_norm()
+
 
 class ResBlock2(nn.Module):
     def __init__(self, channels, kernel_size=3, dilation=(1, 3)):
@@ -41,3 +45,7 @@ class ResBlock2(nn.Module):
         for c in self.convs:
             x = c(x, pre_slope=LRELU_SLOPE, residual=x)
         return x
+
+    def remove_weight_norm(self):
+        for layer in self.convs:
+            layer.remove_weight_norm()

@@ -43,4 +43,12 @@ class Generator(nn.Module):
         return self.forward_cl(mel.transpose(1, 2)).transpose(1, 2)
 
     def remove_weight_norm(self):
-        raise NotImplementedError("inference-time weight-norm removal is outside the training hot path")
+        """reference generator.py:57-64: fold g * v / ||v|| into plain weights (inference).  The GEMM-layout weights
+        and their tensor-core operand images are then baked once, on the first no-grad forward (layers._prepped)."""
+        print("Removing weight norm...")
+        for layer in self.ups:
+            layer.remove_weight_norm()
+        for block in self.resblocks:
+            block.remove_weight_norm()
+        self.conv_pre.remove_weight_norm()
+        self.conv_post.remove_weight_norm()

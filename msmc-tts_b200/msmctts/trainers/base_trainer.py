@@ -6,7 +6,7 @@ import re
 
 import torch
 
-from msmctts.datasets import build_dataloader
+from msmctts.datasets import DevicePrefetcher, build_dataloader
 from msmctts.distributed.distributed import apply_gradient_allreduce
 from msmctts.utils.logger import Logger
 from msmctts.utils.utils import load_checkpoint, to_model
@@ -62,7 +62,9 @@ class BaseTrainer(object):
             epoch = iteration // max(1, len(loader))
             if sampler is not None:
                 sampler.set_epoch(epoch)
-            for batch in loader:
+            # batch i+1 is uploaded from pinned memory on a side stream while step i runs (datasets/prefetch.py)
+            use_prefetch = torch.cuda.is_available() and next(self.model.parameters()).is_cuda
+            for batch in (DevicePrefetcher(loader) if use_prefetch else loader):
                 lr_scheduler.step(self.optimizer, iteration)
                 batch = to_model(batch)
                 self.optimizer.zero_grad()         # reference base_trainer.py:84-85 (set_to_none: no launches)

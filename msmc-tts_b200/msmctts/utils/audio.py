@@ -111,3 +111,42 @@ class TorchSTFT(nn.Module):
         y = self.transform_cl(x)                      # (B, frames, F, C)
         B, T, Fq, Cn = y.shape
         return y.permute(0, 3, 2, 1).reshape(B, Cn * Fq, T), None
+
+
+class MelExtractor(nn.Module):
+    """On-GPU log-mel features in the reference's normalisation (reference
+    examples/csmsc/scripts/audio/audio.py:59-63,114-131 + hparams.py): pre-emphasis 0.97, STFT(n_fft, hop, win,
+    hann, centre / reflect), Slaney mel filterbank (librosa.filters.mel, htk=False -- restated, see
+    trainers/criterions/stft_loss.py), 20 log10(max(1e-5, .)) - ref_level_db, symmetric normalisation to
+    [-max_abs, max_abs].  Replaces the librosa / scipy preprocessing pass: waveforms go to the device once and the
+    features never touch the host.  wav (B, L) -> mel (B, frames, n_mels), frames = L // hop + 1."""
+
+    def __init__(self, sample_rate=24000, n_fft=2048, hop_size=300, win_size=1200, n_mels=80, preemphasis=0.97,
+                 ref_level_db=20.0, min_level_db=-100.0, max_abs_value=4.0):
+        super().__init__()
+        from msmctts.trainers.criterions.stft_loss import mel_filterbank_slaney
+        self.n_fft, self.hop_size, self.win_size, self.n_mels = n_fft, hop_size, win_size, n_mels
+        self.preemphasis, self.ref_level_db = preemphasis, ref_level_db
+        self.min_level_db, self.max_abs_value = min_level_db, max_abs_value
+        self.n_freq = n_fft // 2 + 1
+        basis, self.left, self.n_freq_pad = dft_basis(n_fft, win_size, normalized=False)
+        self.register_buffer("basis", basis, persistent=False)
+        self.register_buffer("basis_t", basis[:win_size].t().contiguous(), persistent=False)
+        mel_g = torch.zeros(self.n_freq_pad, n_mels)
+        mel_g[:self.n_freq] = mel_filterbank_slaney(sample_rate, n_fft, n_mels, 0, sample_rate // 2).t()
+        self.register_buffer("mel_basis_g", mel_g, persistent=False)
+
+    @torch.no_grad()
+    def forward(self, wav):
+        if wav.dim() == 3:
+            wav = wav.squeeze(-1)
+        # y[n] = x[n] - a x[n-1]  (scipy.signal.lfilter([1, -a], [1], x), zero initial state)
+        y = wav - self.preemphasis * torch.nn.functional.pad(wav, (1, 0))[:, :-1]
+        spec = Fn.stft_frames(y.contiguous(), self.basis, self.basis_t, self.hop_size, self.n_fft // 2 - self.left,
+                              self.win_size)
+        mag = Fn.spec_magnitude(spec, 0.0, False)                       # |STFT|, padded width
+        B, T, Fp = mag.shape
+        mel = Fn.conv_cl(mag.reshape(B * T, 1, 1, Fp), self.mel_basis_g, out_channels=self.n_mels)
+        db = 20.0 * torch.log10(mel.reshape(B, T, self.n_mels).clamp_min(1e-5)) - self.ref_level_db
+        s = (2 * self.max_abs_value) * ((db - self.min_level_db) / (-self.min_level_db)) - self.max_abs_value
+        return s.clamp(-self.max_abs_value, self.max_abs_value)

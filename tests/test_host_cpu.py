@@ -304,3 +304,93 @@ def test_batched_lsgan_loss_equals_sum_of_mse_terms():
         ref.backward()
         for a, b in zip(both, ref_in):
             assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-9)
+
+
+def _write_wav(path, x, sr=24000):
+    import wave
+    import numpy as np
+    with wave.open(str(path), "wb") as f:
+        f.setnchannels(1)
+        f.setsampwidth(2)
+        f.setframerate(sr)
+        f.writeframes((np.clip(x, -1, 1) * 32767).astype("<i2").tobytes())
+
+
+def test_file_backed_datasets_follow_the_reference_yaml_interface(tmp_path):
+    """SURVEY 8f rank 4 data path: MelDataset / TTSDataset built from the reference yaml's own `dataset` keys
+    (id_list, feature, feature_path templates and books, dimension, frameshift, padding_value, segment_length,
+    pre_load): windows of mel and wav stay aligned, batches are sorted by length and padded with padding_value."""
+    import numpy as np
+    import torch
+    from msmctts.datasets import build_dataloader
+    from msmctts.utils.config import ConfigItem
+    rng = np.random.default_rng(0)
+    (tmp_path / "mel").mkdir()
+    (tmp_path / "wav").mkdir()
+    ids, lens = ["000001", "000002", "000003", "000004"], [57, 80, 41, 66]
+    hop = 30
+    for uid, n in zip(ids, lens):
+        np.save(tmp_path / "mel" / (uid + ".npy"), rng.standard_normal((n, 8)).astype(np.float32))
+        # sample k of the waveform encodes its own index so alignment can be checked
+        _write_wav(tmp_path / "wav" / (uid + ".wav"), (np.arange(n * hop) % 900) / 2000.0)   # 900 = 30 hops
+    (tmp_path / "train.list").write_text("\n".join(ids) + "\n")
+    phones = {uid: rng.integers(1, 50, size=5 + i) for i, uid in enumerate(ids)}
+    (tmp_path / "phone.txt").write_text("".join(
+        "%s|%s\n" % (u, " ".join("%d_%d_%d" % (p, p % 7 + 1, p % 2) for p in ph)) for u, ph in phones.items()))
+    durs = {}
+    for uid, n in zip(ids, lens):
+        k = len(phones[uid])
+        d = np.full(k, n // k)
+        d[-1] += n - d.sum()
+        durs[uid] = d
+    (tmp_path / "dur.txt").write_text("".join("%s|%s\n" % (u, " ".join(str(int(v)) for v in d))
+                                              for u, d in durs.items()))
+    # ---- MelDataset (examples/csmsc/configs/msmc_vq_gan.yaml: dataset block), random 20-frame segments
+    cfg = ConfigItem({"_name": "MelDataset", "id_list": str(tmp_path / "train.list"), "samplerate": 24000,
+                      "feature": ["mel", "wav"],
+                      "feature_path": [str(tmp_path / "mel" / "{}.npy"), str(tmp_path / "wav" / "{}.wav")],
+                      "dimension": [8, 1], "frameshift": [hop, 1], "padding_value": [-4, 0], "pre_load": False,
+                      "segment_length": 20 * hop})
+    ds, _, loader = build_dataloader(cfg, ConfigItem({"batch_size": 4, "num_workers": 0}))
+    assert len(ds) >= 3200                       # an epoch is at least MIN_DATASET_SIZE draws, like the reference
+    batch = next(iter(loader))
+    assert batch["mel"].shape == (4, 20, 8) and batch["wav"].shape == (4, 20 * hop, 1)
+    assert batch["mel_length"].tolist() == [20] * 4 and batch["wav_length"].tolist() == [20 * hop] * 4
+    w = batch["wav"][:, :, 0] * 2000.0           # recovered sample indices: consecutive, starting at a hop multiple
+    assert torch.allclose((w[:, 1:] - w[:, :-1]) % 900, torch.ones(4, 20 * hop - 1), atol=0.1)
+    assert torch.allclose(torch.round(w[:, 0]) % hop, torch.zeros(4), atol=0.1)
+    # whole utterances: sorted by length, padded
+    cfg["segment_length"] = -1
+    ds, _, loader = build_dataloader(cfg, ConfigItem({"batch_size": 4, "num_workers": 0}))
+    batch = next(iter(loader))
+    got = batch["mel_length"].tolist()           # (a shuffled epoch of >= 3200 draws may repeat an utterance)
+    assert got == sorted(got, reverse=True) and set(got) <= set(lens)
+    assert batch["mel"].shape == (4, got[0], 8) and batch["wav"].shape == (4, got[0] * hop, 1)
+    for row, n in enumerate(got):
+        if n < got[0]:
+            assert float(batch["mel"][row, n:].max()) == -4.0 and float(batch["mel"][row, n:].min()) == -4.0
+            assert float(batch["wav"][row, n * hop:].abs().max()) == 0
+    # ---- TTSDataset (msmc_vq_gan_am.yaml: text and durations come from books)
+    cfg = ConfigItem({"_name": "TTSDataset", "id_list": str(tmp_path / "train.list"), "samplerate": 24000,
+                      "feature": ["text", "dur", "mel"],
+                      "feature_path": [str(tmp_path / "phone.txt"), str(tmp_path / "dur.txt"),
+                                       str(tmp_path / "mel" / "{}.npy")],
+                      "dimension": [3, 1, 8], "padding_value": [0, 0, -4], "frameshift": [None, None, hop],
+                      "pre_load": True, "segment_length": -1})
+    ds, _, loader = build_dataloader(cfg, ConfigItem({"batch_size": 4, "num_workers": 0}))
+    batch = next(iter(loader))
+    tl = batch["text_length"].tolist()
+    assert tl == sorted(tl, reverse=True) and set(tl) <= {5, 6, 7, 8}
+    assert batch["text"].shape == (4, tl[0], 3) and batch["dur"].shape == (4, tl[0])
+    assert batch["dur"].sum(1).tolist() == batch["mel_length"].tolist()       # durations add up to the mel frames
+    for row, n in enumerate(tl):
+        if n < tl[0]:
+            assert float(batch["text"][row, n:].abs().max()) == 0 and float(batch["dur"][row, n:].abs().max()) == 0
+
+
+def test_device_prefetcher_yields_every_batch_in_order():
+    import torch
+    from msmctts.datasets import DevicePrefetcher
+    batches = [{"x": torch.full((2, 3), float(i)), "n": torch.tensor(i)} for i in range(5)]
+    got = list(DevicePrefetcher(batches))        # no CUDA here: pass-through, same order, nothing dropped
+    assert [int(b["n"]) for b in got] == list(range(5)) and all(float(b["x"][0, 0]) == i for i, b in enumerate(got))
