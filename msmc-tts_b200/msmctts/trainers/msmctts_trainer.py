@@ -207,7 +207,10 @@ class VQGANTrainer(BaseTrainer):
             self.optimizer.zero_grad()
             graph = torch.cuda.CUDAGraph()
             from msmctts._b200.functional import MAIN_PRIORITY
-            with torch.cuda.graph(graph, stream=torch.cuda.Stream(priority=MAIN_PRIORITY)):
+            # thread_local: the DataLoader's pin-memory thread (cudaHostAlloc) and NCCL's watchdog keep making CUDA
+            # calls from THEIR threads while this one captures; in the default "global" mode those invalidate the capture
+            with torch.cuda.graph(graph, stream=torch.cuda.Stream(priority=MAIN_PRIORITY),
+                                  capture_error_mode="thread_local"):
                 st["out"] = self._step(*st["inp"], warmup=warmup, gan=gan)
             st["graph"] = graph
         st["graph"].replay()
