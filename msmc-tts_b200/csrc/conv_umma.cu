@@ -1732,7 +1732,12 @@ extern "C" int msmc_conv_forward_umma_reuse(const msmc_conv_geom* gp, const floa
     switch (BN) {
       case 32: if (two_ctas) LAUNCH_RU(32, true, 1, 6); else LAUNCH_RU(32, true, 3, 6); break;   // 48|144 KB + 48 KB
       case 64: if (two_ctas) LAUNCH_RU(64, true, 1, 3); else LAUNCH_RU(64, true, 3, 4); break;   // 48|144 KB + 48|64 KB
-      default: LAUNCH_RU(128, true, 2, 3); break;    //  96 KB + 96 KB
+      default: {
+        // MSMC_REUSE128_TWO=1 (experiment): single operand stage + 2 weight stages = 112 KB -> two CTAs per SM
+        static const int two128 = [] { const char* e = getenv("MSMC_REUSE128_TWO"); return e ? atoi(e) : 0; }();
+        if (two128) LAUNCH_RU(128, true, 1, 2); else LAUNCH_RU(128, true, 2, 3);    //  96 KB + 96 KB
+        break;
+      }
     }
   } else {
     switch (BN) {

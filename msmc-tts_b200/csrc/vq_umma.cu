@@ -1,6 +1,5 @@
-// Two-phase multi-head VQ search on the tensor cores  (EXPERIMENTAL: selected with MSMC_VQ_UMMA=1, default off;
-// written at the end of round 1 without GPU time left -- to be validated against oracle/vq_oracle.c on a B200 first,
-// tests/pending/gpu_vq_umma.py).
+// Two-phase multi-head VQ search on the tensor cores (msmc_vq_search_umma; validated bit-exact against
+// oracle/vq_oracle.c by tests/test_vq_umma_gpu.py).
 //
 // The CUDA-core search kernels (vq.cu) are fp32-FMA bound: at K = 256 a row costs 65 536 FMAs per 3 360 bytes, so the
 // exhaustive search tops out near 28 % of the HBM roofline.  Here
@@ -15,8 +14,11 @@
 //            argmin is always in that set and the set is a singleton for > 99.9 % of the rows).  Rows with more than
 //            one candidate re-score the candidates with the oracle's exact arithmetic and tie rule (lowest index).
 // The result is identical to the exhaustive fp32 search by construction.
-// Heads of a row tile form a thread-block cluster; the commitment term's head sum goes through distributed shared
-// memory in head order, as in vq_search_cluster_kernel.
+// PERSISTENT: the heads of a row tile form a thread-block cluster (CTA = head) and a cluster walks the row tiles
+// t = blockIdx.x, blockIdx.x + gridDim.x, ...  Each CTA stages ITS head's codebook (hi / lo planes, exact norms) in
+// shared memory ONCE and keeps it for every tile (the one-tile-per-CTA form re-read 64 KB of codebook per 128 rows:
+// more L2 traffic than the rows themselves).  The commitment term's head sum goes through distributed shared memory
+// in head order, as in vq_search_cluster_kernel.
 #include "umma.cuh"
 #include <algorithm>
 #include <cooperative_groups.h>
@@ -32,17 +34,20 @@ constexpr int VU_THREADS = VU_PRODUCERS + 32;  // + the MMA warp
 constexpr int VU_MAX_CAND = 4;               // candidates kept per row half before the exhaustive fallback
 constexpr int VU_DV_LD = VU_DIM + 1;         // padded row pitch of the (q - z)^2 tile: a warp's 32 rows hit 32 banks
 
-// A and B planes use different shared-memory layouts, hence different descriptor high words
-__device__ __forceinline__ void umma_tf32_kmaj_a_mnmaj_b(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
-                                                         uint32_t accumulate) {
+// A and B planes use different shared-memory layouts, hence different descriptor high words; convergent predicated
+// issue (see umma_tf32_pred in umma.cuh)
+__device__ __forceinline__ void umma_tf32_kmaj_a_mnmaj_b_pred(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32,
+                                                              uint32_t idesc, uint32_t accumulate, uint32_t elected) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
       "mov.b64 da, {%1, %5};\n\t"
       "mov.b64 db, {%2, %6};\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
       :
-      : "r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "n"(DESC_HI_K), "n"(DESC_HI_MN)
+      : "r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "n"(DESC_HI_K), "n"(DESC_HI_MN),
+        "r"(elected)
       : "memory");
 }
 
@@ -55,15 +60,25 @@ __device__ __forceinline__ float exact_dist(const float (&zr)[VU_DIM], float zz,
   return (zz - 2.f * dot) + eek;
 }
 
-// dims D0 .. D0+31 of one row: gather the chosen codeword, write quant_raw / quant_st, leave (q - z)^2 in `dv`
-template <int D0>
-__device__ __forceinline__ void emit_row_half(const float (&zr)[VU_DIM], const float* __restrict__ e_h, int K, int k,
+// exact fp32 codeword element (dim d, codeword k) from the resident operand planes: hi + lo is exact by construction
+template <int K>
+__device__ __forceinline__ float cb_elem(const uint8_t* __restrict__ sB, int d, int k) {
+  constexpr int B_PLANE = (K / 32) * 4096;
+  const int half = d >> 5, p = d & 31, c = k >> 2;
+  const uint8_t* a = sB + (half * 2) * B_PLANE + (uint32_t)(c >> 3) * 4096u + mn_off(p, c & 7) + (uint32_t)(k & 3) * 4u;
+  return *reinterpret_cast<const float*>(a) + *reinterpret_cast<const float*>(a + B_PLANE);
+}
+
+// dims D0 .. D0+31 of one row: gather the chosen codeword (from shared memory), write quant_raw / quant_st, leave
+// (q - z)^2 in `dv`
+template <int K, int D0>
+__device__ __forceinline__ void emit_row_half(const float (&zr)[VU_DIM], const uint8_t* __restrict__ sB, int k,
                                               bool row_ok, int row, int r, int n_heads, int h,
                                               float* __restrict__ quant_raw, float* __restrict__ quant_st,
                                               float* __restrict__ dv) {
   float q[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) q[j] = __ldg(e_h + (size_t)(D0 + j) * K + k);
+  for (int j = 0; j < 32; ++j) q[j] = cb_elem<K>(sB, D0 + j, k);
   if (row_ok) {
     float* qr = quant_raw + (int64_t)row * (n_heads * VU_DIM) + h * VU_DIM + D0;
     float* qs = quant_st + (int64_t)row * (n_heads * VU_DIM) + h * VU_DIM + D0;
@@ -113,7 +128,7 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_heads = gridDim.y, h = blockIdx.y;
-  const int row0 = blockIdx.x * VU_ROWS;
+  const int n_tiles = (n_rows + VU_ROWS - 1) / VU_ROWS;
   const float* e_h = embed + (size_t)h * VU_DIM * K;
   constexpr int MMA_WARP = VU_PRODUCERS / 32;
 
@@ -134,7 +149,43 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp < MMA_WARP) {
-    // ================================ operand staging (once: the whole K extent is 64) ================================
+    // ============ once per CTA: this head's codebook -> hi / lo operand planes, exact norms, max norm ============
+    // B: 64 dims x K/4 chunks of 4 consecutive codewords, read straight from the dim-major codebook
+#pragma unroll 4
+    for (int i = 0; i < (VU_DIM * (K / 4)) / VU_PRODUCERS; ++i) {
+      const int e = tid + VU_PRODUCERS * i;
+      const int d_ = e / (K / 4), c = e - d_ * (K / 4);
+      const int half = d_ >> 5, p = d_ & 31, nblk = c >> 3, c16 = c & 7;
+      const float4 x = __ldg(reinterpret_cast<const float4*>(e_h + (size_t)d_ * K + c * 4));
+      const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+      uint8_t* d = sB + (half * 2) * B_PLANE + (uint32_t)nblk * 4096u + mn_off(p, c16);
+      *reinterpret_cast<float4*>(d) = hi;
+      *reinterpret_cast<float4*>(d + B_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+    }
+    // exact codeword norms, the oracle's order (sequential fma over d)
+    for (int k = tid; k < K; k += VU_PRODUCERS) {
+      float s = 0.f;
+#pragma unroll 8
+      for (int d_ = 0; d_ < VU_DIM; ++d_) { const float v = __ldg(e_h + (size_t)d_ * K + k); s = fmaf(v, v, s); }
+      ee[k] = s;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(VU_PRODUCERS) : "memory");
+    if (warp == 0) {
+      float m = 0.f;
+      for (int k = lane; k < K; k += 32) m = fmaxf(m, ee[k]);
+      m = warp_max(m);
+      if (lane == 0) ee_max[0] = m;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(VU_PRODUCERS) : "memory");      // ee_max visible
+  }
+  const float inv_heads = 1.f / (float)n_heads;
+  const uint32_t elected = elect_one();
+
+  uint32_t par = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1u) {
+  const int row0 = tile * VU_ROWS;
+  if (warp < MMA_WARP) {
+    // ================================ operand staging: this tile's rows ================================
     // A: 128 rows x 16 sixteen-byte chunks; consecutive threads read consecutive chunks of a row (256 B per row)
 #pragma unroll
     for (int i = 0; i < (VU_ROWS * 16) / VU_PRODUCERS; ++i) {
@@ -150,34 +201,7 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
       *reinterpret_cast<float4*>(d) = hi;
       *reinterpret_cast<float4*>(d + A_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
     }
-    // B: 64 dims x K/4 chunks of 4 consecutive codewords, read straight from the dim-major codebook
-#pragma unroll 4
-    for (int i = 0; i < (VU_DIM * (K / 4)) / VU_PRODUCERS; ++i) {
-      const int e = tid + VU_PRODUCERS * i;
-      const int d_ = e / (K / 4), c = e - d_ * (K / 4);
-      const int half = d_ >> 5, p = d_ & 31, nblk = c >> 3, c16 = c & 7;
-      const float4 x = __ldg(reinterpret_cast<const float4*>(e_h + (size_t)d_ * K + c * 4));
-      const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-      uint8_t* d = sB + (half * 2) * B_PLANE + (uint32_t)nblk * 4096u + mn_off(p, c16);
-      *reinterpret_cast<float4*>(d) = hi;
-      *reinterpret_cast<float4*>(d + B_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
-    }
-    publish_and_arrive_warp(full_bar);
-
-    // exact codeword norms, the oracle's order (sequential fma over d)
-    for (int k = tid; k < K; k += VU_PRODUCERS) {
-      float s = 0.f;
-#pragma unroll 8
-      for (int d_ = 0; d_ < VU_DIM; ++d_) { const float v = __ldg(e_h + (size_t)d_ * K + k); s = fmaf(v, v, s); }
-      ee[k] = s;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(VU_PRODUCERS) : "memory");
-    if (warp == 0) {
-      float m = 0.f;
-      for (int k = lane; k < K; k += 32) m = fmaxf(m, ee[k]);
-      m = warp_max(m);
-      if (lane == 0) ee_max[0] = m;
-    }
+    publish_and_arrive_warp(full_bar);      // (on the first tile this also publishes the codebook planes)
 
     // ================================ phase 2: one thread per (row, column half) ================================
     const int lane_grp = warp & 3, chalf = warp >> 2;
@@ -194,130 +218,124 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
     float zz = 0.f;
 #pragma unroll
     for (int d_ = 0; d_ < VU_DIM; ++d_) zz = fmaf(zr[d_], zr[d_], zz);
-    asm volatile("bar.sync 1, %0;" ::"n"(VU_PRODUCERS) : "memory");      // ee_max visible
     const float emax = ee_max[0];
     const float delta2 = 2.f * 9.5367431640625e-07f * (zz + emax + 2.f * sqrtf(zz * emax));   // 2 * 2^-20 * (|z| + |e|)^2
 
-    mbar_wait(accum_bar, 0);
+    mbar_wait(accum_bar, par);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
     constexpr int CH = K / 2;                           // columns per thread
     const int cbeg = chalf * CH;
-    float best = INFINITY;
-#pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + CH; c0 += 16) {
-      float acc[16];
-      tmem_ld16(taddr + (uint32_t)c0, acc);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) best = fminf(best, (zz - 2.f * acc[j]) + ee[c0 + j]);
-    }
-    row_best[chalf * VU_ROWS + r] = best;
-    asm volatile("bar.sync 1, %0;" ::"n"(VU_PRODUCERS) : "memory");
-    const float thr = fminf(row_best[r], row_best[VU_ROWS + r]) + delta2;
-    int cnt = 0;
-    int mine[VU_MAX_CAND];
+    // ONE pass over this thread's K/2 columns: smallest approximate distance (lowest index on ties), its index, and
+    // the second smallest value.  A row whose runner-up (over both halves) lies more than 2*delta above its best has a
+    // single candidate -- the exhaustive fp32 search's argmin (tests/test_vq_two_phase_margin.py); any other row is
+    // re-scored exactly over all K codewords (< 0.1 % of the rows).
+    float best = INFINITY, second = INFINITY;
+    int best_c = 0x7fffffff;
 #pragma unroll 1
     for (int c0 = cbeg; c0 < cbeg + CH; c0 += 16) {
       float acc[16];
       tmem_ld16(taddr + (uint32_t)c0, acc);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        if ((zz - 2.f * acc[j]) + ee[c0 + j] <= thr) {
-#pragma unroll
-          for (int s = 0; s < VU_MAX_CAND; ++s)
-            if (cnt == s) mine[s] = c0 + j;              // (static indices: the list stays in registers)
-          ++cnt;
-        }
+        const float dj = (zz - 2.f * acc[j]) + ee[c0 + j];
+        if (dj < best) { second = best; best = dj; best_c = c0 + j; }
+        else second = fminf(second, dj);
       }
     }
-    cand_cnt[chalf * VU_ROWS + r] = cnt;
-#pragma unroll
-    for (int j = 0; j < VU_MAX_CAND; ++j)
-      if (j < cnt) cand_idx[(chalf * VU_ROWS + r) * VU_MAX_CAND + j] = mine[j];
+    row_best[chalf * VU_ROWS + r] = best;
+    cand_cnt[chalf * VU_ROWS + r] = best_c;
+    reinterpret_cast<float*>(cand_idx)[chalf * VU_ROWS + r] = second;
     asm volatile("bar.sync 1, %0;" ::"n"(VU_PRODUCERS) : "memory");
-    tc_fence_before();
 
-    if (chalf == 0) {
-      // the row's owner decides: one candidate -> done; a few -> exact re-score in ascending index order (lowest
-      // index wins ties, like the exhaustive search); too many to have been recorded, or none (NaN input) ->
-      // exhaustive exact search
-      const int c_lo = cand_cnt[r], c_hi = cand_cnt[VU_ROWS + r];
-      int best_k;
-      if (c_lo + c_hi == 1) {
-        best_k = c_lo ? cand_idx[r * VU_MAX_CAND] : cand_idx[(VU_ROWS + r) * VU_MAX_CAND];
-      } else if (c_lo + c_hi >= 2 && c_lo <= VU_MAX_CAND && c_hi <= VU_MAX_CAND) {
+    if (chalf == 0) {                                    // (warp-uniform) the row's owner merges the two halves
+      const float b0 = row_best[r], b1 = row_best[VU_ROWS + r];
+      const float s0 = reinterpret_cast<const float*>(cand_idx)[r], s1 = reinterpret_cast<const float*>(cand_idx)[VU_ROWS + r];
+      const int k0 = cand_cnt[r], k1 = cand_cnt[VU_ROWS + r];
+      const bool lo_wins = b0 <= b1;                     // ties: the lower half holds the lower indices
+      const float bmin = lo_wins ? b0 : b1;
+      const float runner = fminf(lo_wins ? b1 : b0, fminf(s0, s1));
+      int best_k = lo_wins ? k0 : k1;
+      const bool amb = !(runner > bmin + delta2) || (unsigned)best_k >= (unsigned)K;
+      if (__any_sync(0xffffffffu, amb)) {
+        // some row of this warp is ambiguous (or NaN / Inf): the warp re-reads its rows' K dot products
+        // (tcgen05.ld is warp-collective) and the ambiguous lanes re-score every codeword within 2*delta of their
+        // minimum with the oracle's exact arithmetic, in ascending index order (lowest index wins ties)
+        const float thr = bmin + delta2;
         float bd = INFINITY;
-        best_k = 0x7fffffff;
-        for (int half2 = 0; half2 < 2; ++half2) {
-          const int n = half2 ? c_hi : c_lo;
-          for (int j = 0; j < n; ++j) {
-            const int k = cand_idx[(half2 * VU_ROWS + r) * VU_MAX_CAND + j];
-            const float dk = exact_dist(zr, zz, e_h, K, k, ee[k]);
-            if (dk < bd) { bd = dk; best_k = k; }        // ascending k: strict < keeps the lowest index on ties
+        int bk = 0x7fffffff;
+#pragma unroll 1
+        for (int c0 = 0; c0 < K; c0 += 16) {
+          float acc[16];
+          tmem_ld16(taddr + (uint32_t)c0, acc);
+          if (amb) {
+#pragma unroll 1
+            for (int j = 0; j < 16; ++j) {
+              if ((zz - 2.f * acc[j]) + ee[c0 + j] <= thr) {
+                const float dk = exact_dist(zr, zz, e_h, K, c0 + j, ee[c0 + j]);
+                if (dk < bd) { bd = dk; bk = c0 + j; }
+              }
+            }
           }
         }
-      } else {
-        float bd = INFINITY;
-        best_k = 0;
-        for (int k = 0; k < K; ++k) {
-          const float dk = exact_dist(zr, zz, e_h, K, k, ee[k]);
-          if (dk < bd) { bd = dk; best_k = k; }
-        }
+        if (amb) best_k = ((unsigned)bk < (unsigned)K) ? bk : 0;     // no candidate at all (NaN row): index 0
       }
       row_idx[r] = best_k;
       if (row_ok) idx[(int64_t)row * n_heads + h] = (int64_t)best_k;
     }
+    tc_fence_before();                                   // this thread's TMEM reads of the tile are complete
     asm volatile("bar.sync 1, %0;" ::"n"(VU_PRODUCERS) : "memory");
     // gather, straight-through output and per-row squares: the two threads of a row take 32 dims each.
     // (dv aliases the A operand: every MMA that read it has completed -- accum_bar -- and all threads are past it)
+    // (sB is never overwritten; dv aliases sA, so the codeword is gathered into registers BEFORE dv is written --
+    //  emit_row_half reads sB only)
     if (chalf == 0)
-      emit_row_half<0>(zr, e_h, K, row_idx[r], row_ok, row, r, n_heads, h, quant_raw, quant_st, dv);
+      emit_row_half<K, 0>(zr, sB, row_idx[r], row_ok, row, r, n_heads, h, quant_raw, quant_st, dv);
     else
-      emit_row_half<32>(zr, e_h, K, row_idx[r], row_ok, row, r, n_heads, h, quant_raw, quant_st, dv);
+      emit_row_half<K, 32>(zr, sB, row_idx[r], row_ok, row, r, n_heads, h, quant_raw, quant_st, dv);
   } else {
-    // ================================ MMA issuer ================================
+    // ================================ MMA issuer (convergent, predicated issue) ================================
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) |      // D f32, A/B tf32, B MN-major
                                ((uint32_t)(K >> 3) << 17) | ((uint32_t)(VU_ROWS >> 4) << 24);
-    if (lane == 0) {
-      mbar_wait(full_bar, 0);
-      tc_fence_after();
-      const uint32_t a0 = desc_lo_k(smem_u32(sA)), b0 = desc_lo_mn(smem_u32(sB));
+    mbar_wait(full_bar, par);
+    tc_fence_after();
+    const uint32_t a0 = desc_lo_k(smem_u32(sA)), b0 = desc_lo_mn(smem_u32(sB));
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint32_t ad = a0 + (uint32_t)(half * 2) * (A_PLANE >> 4);
-        const uint32_t bd = b0 + (uint32_t)(half * 2) * (B_PLANE >> 4);
+    for (int half = 0; half < 2; ++half) {
+      const uint32_t ad = a0 + (uint32_t)(half * 2) * (A_PLANE >> 4);
+      const uint32_t bd = b0 + (uint32_t)(half * 2) * (B_PLANE >> 4);
 #pragma unroll
-        for (int kg = 0; kg < 4; ++kg) {
-          // 8 dims per MMA: A advances 32 B along its 128-byte rows (2 units), B two 4-row atoms (1 KB = 64 units)
-          const uint32_t a_hi = ad + 2 * kg, b_hi = bd + 64 * kg;
-          const uint32_t a_lo = a_hi + (A_PLANE >> 4), b_lo = b_hi + (B_PLANE >> 4);
-          umma_tf32_kmaj_a_mnmaj_b(tmem_base, a_lo, b_hi, IDESC, (half > 0 || kg > 0) ? 1u : 0u);
-          umma_tf32_kmaj_a_mnmaj_b(tmem_base, a_hi, b_lo, IDESC, 1u);
-          umma_tf32_kmaj_a_mnmaj_b(tmem_base, a_hi, b_hi, IDESC, 1u);
-        }
+      for (int kg = 0; kg < 4; ++kg) {
+        // 8 dims per MMA: A advances 32 B along its 128-byte rows (2 units), B two 4-row atoms (1 KB = 64 units)
+        const uint32_t a_hi = ad + 2 * kg, b_hi = bd + 64 * kg;
+        const uint32_t a_lo = a_hi + (A_PLANE >> 4), b_lo = b_hi + (B_PLANE >> 4);
+        umma_tf32_kmaj_a_mnmaj_b_pred(tmem_base, a_lo, b_hi, IDESC, (half > 0 || kg > 0) ? 1u : 0u, elected);
+        umma_tf32_kmaj_a_mnmaj_b_pred(tmem_base, a_hi, b_lo, IDESC, 1u, elected);
+        umma_tf32_kmaj_a_mnmaj_b_pred(tmem_base, a_hi, b_hi, IDESC, 1u, elected);
       }
-      umma_commit(accum_bar);
     }
+    umma_commit_pred(accum_bar, elected);
     __syncwarp();
   }
+  // head sum of the commitment term in head order through distributed shared memory (cluster = the heads of this tile)
+  __syncthreads();
+  cluster.sync();
+  const int rows_here = min(VU_ROWS, n_rows - row0);
+  // this CTA combines the rows ri = h, h + n_heads, ...
+  const int my_rows = (rows_here - h + n_heads - 1) / n_heads;
+  for (int e = tid; e < my_rows * VU_DIM; e += VU_THREADS) {
+    const int ri = (e >> 6) * n_heads + h, d_ = e & (VU_DIM - 1);
+    float acc = *cluster.map_shared_rank(dv + ri * VU_DV_LD + d_, 0);
+    for (int hh = 1; hh < n_heads; ++hh) acc = __fadd_rn(acc, *cluster.map_shared_rank(dv + ri * VU_DV_LD + d_, hh));
+    diff[(int64_t)(row0 + ri) * VU_DIM + d_] = acc * inv_heads;
+  }
+  cluster.sync();     // nobody overwrites its tile (next A staging) or exits while a neighbour may still read it
+  }   // tile loop
   __syncthreads();
   if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)K) : "memory");
   }
-  // head sum of the commitment term in head order through distributed shared memory (cluster = the heads of this tile)
-  cluster.sync();
-  const float inv_heads = 1.f / (float)n_heads;
-  const int rows_here = min(VU_ROWS, n_rows - row0);
-  for (int e = tid; e < VU_ROWS * VU_DIM; e += VU_THREADS) {
-    const int ri = e / VU_DIM, d_ = e - ri * VU_DIM;
-    if (ri < rows_here && (ri % n_heads) == h) {
-      float acc = *cluster.map_shared_rank(dv + ri * VU_DV_LD + d_, 0);
-      for (int hh = 1; hh < n_heads; ++hh) acc = __fadd_rn(acc, *cluster.map_shared_rank(dv + ri * VU_DV_LD + d_, hh));
-      diff[(int64_t)(row0 + ri) * VU_DIM + d_] = acc * inv_heads;
-    }
-  }
-  cluster.sync();     // nobody exits while a neighbour may still read its shared memory
 }
 
 template <int K>
@@ -327,7 +345,9 @@ int launch_vq_umma(const float* z, int64_t ld_z, const float* embed, float* quan
   const size_t smem = 1024 + 4 * (size_t)VU_ROWS * 128 + 4 * (size_t)NB * 4096 + (size_t)K * 4 +
                       2 * VU_ROWS * 4 + 2 * VU_ROWS * 4 + 2 * VU_ROWS * VU_MAX_CAND * 4 + VU_ROWS * 4 + 8 + 16 + 16;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)ceil_div(n_rows, VU_ROWS), (unsigned)n_heads, 1);
+  // persistent: one cluster (n_heads CTAs, one per SM) per slot, each walking its share of the row tiles
+  const int n_clusters = std::max(1, std::min(ceil_div(n_rows, VU_ROWS), num_sms() / n_heads));
+  cfg.gridDim = dim3((unsigned)n_clusters, (unsigned)n_heads, 1);
   cfg.blockDim = dim3(VU_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
