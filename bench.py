@@ -591,11 +591,15 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
+    # the first three calls are eager (the graph is captured on the fourth): count the kernels of the THIRD one, a
+    # steady-state step (the first step builds operand images inline, later ones batch them in the weight prefetch)
+    step_resident(0)
+    step_resident(1)
     l0 = L.launch_count
-    step_resident(0)                  # first call is always eager: count the kernels one step launches
+    step_resident(2)
     launches = L.launch_count - l0
-    for i in range(max(3, args.warmup) + 3):     # +3: eager warm-ups before the graph is captured
-        step_resident(1 + i)
+    for i in range(max(3, args.warmup) + 1):
+        step_resident(3 + i)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_step = timed(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
@@ -618,6 +622,11 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         L.profile_begin()
     for i in range(2):
+        # An eager step is ~2000 ctypes calls at ~40 us of host time each: on an idle GPU an event pair around a call
+        # would time the HOST (the start event fires long before the launch arrives).  A spin kernel keeps the device
+        # busy while the host enqueues the step, so every event pair brackets back-to-back device work only.
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(0.16 * 1.9e9))
         step_resident(100 + i)
     torch.cuda.synchronize()
     if rank == 0:

@@ -1517,8 +1517,15 @@ bool wgrad_reuse_plan(const msmc_conv_geom& g, bool split, WgradReusePlan* p) {
   if (g.Cs % 32 != 0 || g.Cd % 32 != 0 || p->n_taps < 3) return false;
   const int TG = (p->n_taps + 3) / 4;
   if (WR_POS + (4 * TG - 1) * p->tap_stride > WR_ROWS) return false;
+  // N tile: the tensor pipe spends ~20 cycles per MMA on top of the operand reads (measured: 60 / 68 / 85 cycles for
+  // N = 32 / 64 / 128), so the widest tile that fits the accumulator groups into the 512 TMEM columns wins
+  static const int wide = [] { const char* e = getenv("MSMC_WGRAD_REUSE_BN128"); return e ? atoi(e) : 1; }();
   p->bn = (g.Cd % 64 == 0) ? 64 : 32;
   p->kc_cta = ((g.Cs / 32) % 2 == 0) ? 2 : 1;
+  if (wide && g.Cd % 128 == 0) {
+    if (p->kc_cta * TG * 128 <= 512) p->bn = 128;
+    else if (TG * 128 <= 512) { p->bn = 128; p->kc_cta = 1; }
+  }
   if (p->kc_cta * TG * p->bn > 512) p->kc_cta = 1;
   if (p->kc_cta * TG * p->bn > 512) return false;
   const int Ld = g.Hd * g.Wd;
@@ -1594,8 +1601,11 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
     else if (rxfc == XFC_LRELU) LAUNCH_WR_X(BN_, SPLIT_, XFC_LRELU);   \
     else LAUNCH_WR_X(BN_, SPLIT_, XFC_GENERIC);                        \
   } while (0)
-      if (split) { if (rp.bn == 64) LAUNCH_WR(64, true); else LAUNCH_WR(32, true); }
-      else { if (rp.bn == 64) LAUNCH_WR(64, false); else LAUNCH_WR(32, false); }
+      if (split) {
+        if (rp.bn == 128) LAUNCH_WR(128, true); else if (rp.bn == 64) LAUNCH_WR(64, true); else LAUNCH_WR(32, true);
+      } else {
+        if (rp.bn == 128) LAUNCH_WR(128, false); else if (rp.bn == 64) LAUNCH_WR(64, false); else LAUNCH_WR(32, false);
+      }
 #undef LAUNCH_WR
 #undef LAUNCH_WR_X
       MSMC_CHECK_LAUNCH();
