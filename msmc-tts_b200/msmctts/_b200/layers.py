@@ -62,14 +62,21 @@ def _prepped(mod, v, g, transposed=False, swap_taps=False):
 warnings.filterwarnings("ignore", message="The AccumulateGrad node's stream does not match")
 
 
+import os
+
+PREFETCH_GROUP_BYTES = int(os.environ.get("MSMC_PF_GROUP_MB", "8")) << 20
+
+
 def prefetch_weights(root):
     """Re-parametrise every conv / linear weight under `root` (and rebuild the tensor-core operand images each
     layer used on its previous call) on a dedicated side stream, in module order, ahead of the forward pass.
 
-    One step runs ~700 of these 3-10 us launches; issued inline they sit on the critical path in front of every
-    conv.  Here they overlap the convolutions of earlier layers: each layer's entry carries an event and the
-    consuming stream waits only for its own weight.  Must be called inside a `prep_scope()`; returns the side
-    stream (the caller joins it before the step ends) or None when there is nothing to do."""
+    Issued inline these are ~700 launches of 3-10 us per step in front of every conv.  Here the layers are walked
+    WITHOUT launching (each layer's autograd node and output buffers are created, the work is recorded as a job),
+    and every ~8 MB of operands the recorded jobs run as two multi-tensor launches (msmc_weight_norm_fwd_multi,
+    msmc_weight_image_multi) on the side stream; the layers of a group share one event and a consuming stream waits
+    only for its own group.  Must be called inside a `prep_scope()`; returns the side stream (the caller joins it
+    before the step ends) or None when there is nothing to do."""
     if Fn.PREP_SCOPE[0] == 0 or not Fn.PREFETCH_WEIGHTS:
         return None
     mods = [m for m in root.modules() if hasattr(m, "_prep_spec")]
@@ -79,9 +86,28 @@ def prefetch_weights(root):
     side = Fn.prefetch_stream(cur)
     side.wait_stream(cur)
     Fn.PREFETCHING[0] = True
-    jobs = {"wn": [], "img": []}
-    Fn.DEFERRED[0] = jobs
-    tokens = []
+    # the n-th prefetch of `root` inside one step keeps its own pointer-table staging (D is prefetched twice per step:
+    # before its own update and again, frozen, for the generator step)
+    seen = root.__dict__.get("_msmc_pf_calls")
+    nth = seen[1] + 1 if (seen is not None and seen[0] == Fn.PREP_SCOPE[0]) else 0
+    root.__dict__["_msmc_pf_calls"] = (Fn.PREP_SCOPE[0], nth)
+    state = {"jobs": {"wn": [], "img": []}, "tokens": [], "bytes": 0, "group": 0}
+
+    def flush():
+        # two launches for the whole group (round 1: one per layer and per image, ~700 per train step); the group's
+        # consumers wait on ONE event.  Groups are cut by operand bytes so that the first layers of the forward pass
+        # do not wait for the re-parametrisation of the whole network.
+        Fn.DEFERRED[0] = None
+        if state["tokens"]:
+            Fn.flush_deferred(state["jobs"], (id(root), nth, state["group"]))
+            ev = torch.cuda.Event()
+            ev.record(side)
+            for token in state["tokens"]:
+                token["event"] = ev
+        state.update(jobs={"wn": [], "img": []}, tokens=[], bytes=0, group=state["group"] + 1)
+        Fn.DEFERRED[0] = state["jobs"]
+
+    Fn.DEFERRED[0] = state["jobs"]
     try:
         with torch.cuda.stream(side):
             for m in mods:
@@ -92,21 +118,14 @@ def prefetch_weights(root):
                 token = m.__dict__["_msmc_prep"][2]
                 if token.get("event") is not None or token.get("inline"):
                     continue                       # already prepared in this scope
-                for key in m.__dict__.get("_msmc_img_keys", ()):
+                keys = m.__dict__.get("_msmc_img_keys", ())
+                for key in keys:
                     Fn._weight_image(w, *key)
-                tokens.append(token)
-            Fn.DEFERRED[0] = None
-            # two launches for the whole sub-network (were ~270 + ~430 per train step)
-            # (the n-th prefetch of `root` inside one step keeps its own pointer-table staging: D is prefetched
-            # twice per step, before its own update and again, frozen, for the generator step)
-            seen = root.__dict__.get("_msmc_pf_calls")
-            nth = seen[1] + 1 if (seen is not None and seen[0] == Fn.PREP_SCOPE[0]) else 0
-            root.__dict__["_msmc_pf_calls"] = (Fn.PREP_SCOPE[0], nth)
-            Fn.flush_deferred(jobs, (id(root), nth))
-            ev = torch.cuda.Event()
-            ev.record(side)
-            for token in tokens:
-                token["event"] = ev
+                state["tokens"].append(token)
+                state["bytes"] += w.numel() * 4 * (1 + 2 * len(keys))
+                if state["bytes"] >= PREFETCH_GROUP_BYTES:
+                    flush()
+            flush()
     finally:
         Fn.DEFERRED[0] = None
         Fn.PREFETCHING[0] = False

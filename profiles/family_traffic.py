@@ -13,13 +13,13 @@ import sys
 # kernels launched by each C-ABI entry point (msmc-tts_b200/csrc)
 FAMILY = [
     (r"conv_wgrad_umma_kernel|conv_wgrad_reuse_kernel", "msmc_conv_wgrad_umma"),
-    (r"conv_umma_reuse_kernel", "msmc_conv_forward_umma_reuse"),
+    (r"conv_umma_reuse_kernel|conv_reuse_persist_kernel", "msmc_conv_forward_umma_reuse"),
     (r"conv_umma_kernel", "msmc_conv_forward_umma"),
     (r"conv_gemm_kernel|conv_direct_small_kernel|conv_c1_kernel", "msmc_conv_forward"),
     (r"conv_wgrad_kernel|conv_wgrad_small_kernel", "msmc_conv_wgrad"),
     (r"wgrad_reduce_kernel", "wgrad_reduce (second pass of both weight-gradient entry points)"),
-    (r"weight_image_kernel", "msmc_weight_image"),
-    (r"weight_norm_fwd_kernel", "msmc_weight_norm_fwd"),
+    (r"weight_image_kernel|weight_image_multi_kernel", "msmc_weight_image(_multi)"),
+    (r"weight_norm_fwd_kernel|weight_norm_fwd_multi_kernel", "msmc_weight_norm_fwd(_multi)"),
     (r"weight_norm_bwd_kernel", "msmc_weight_norm_bwd"),
     (r"reflect_fold_kernel", "msmc_reflect_pad_fold"),
     (r"attention_bwd", "msmc_attention_bwd"),
@@ -30,7 +30,7 @@ FAMILY = [
     (r"vq_ema", "msmc_vq_ema_update"),
     (r"vq_backward", "msmc_vq_backward"),
     (r"xform_apply", "msmc_xform_apply"),
-    (r"adam_multi", "msmc_adam_multi"),
+    (r"adam_multi|adam_prepare", "msmc_adam_multi"),
     (r"l1_multi", "msmc_l1_multi"),
 ]
 

@@ -7,9 +7,12 @@ import sys
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5]
 hdr = rows[0]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+mi = hdr.index("Metric Name") if "Metric Name" in hdr else None
 tot = collections.Counter()
 cnt = collections.Counter()
 for r in rows[1:]:
+    if mi is not None and r[mi] != "gpu__time_duration.sum":
+        continue                      # captures with several metrics per launch: durations only
     try:
         v = float(r[vi].replace(",", ""))
     except ValueError:
