@@ -4,21 +4,17 @@
 // The CUDA-core search kernels (vq.cu) are fp32-FMA bound: at K = 256 a row costs 65 536 FMAs per 3 360 bytes, so the
 // exhaustive search tops out near 28 % of the HBM roofline.  Here
 //   phase 1  scores a 128-row tile of one head against all K codewords with tcgen05.mma (3xTF32: fp32-accurate to
-//            ~2^-21 relative, accumulators in TMEM): A = z rows, K-major SWIZZLE_128B (like conv_umma_kernel);
-//            B = the head's codebook straight from its dim-major `embed` buffer, MN-major SWIZZLE_128B_BASE32B
-//            (like the weight-gradient kernel's operands: a 128-byte shared-memory row = 32 consecutive codewords of
-//            one dim), two K halves of 32 dims;
+//            ~2^-21 relative, accumulators in TMEM): A = z rows, B = the head's codebook, both K-major SWIZZLE_128B
+//            (a 128-byte shared-memory row = 32 dims of one row / one codeword), two K halves of 32 dims;
 //   phase 2  reads the 128 x K dot products from TMEM, forms dist = (|z|^2 - 2 z.e_k) + |e_k|^2 with the exact
-//            (sequential-fma) norms, and keeps every codeword within 2*delta of the row minimum,
-//            delta = 2^-20 (|z|^2 + max|e|^2 + 2 |z| max|e|) (tests/test_vq_two_phase_margin.py: the exhaustive search's
-//            argmin is always in that set and the set is a singleton for > 99.9 % of the rows).  Rows with more than
-//            one candidate re-score the candidates with the oracle's exact arithmetic and tie rule (lowest index).
+//            (sequential-fma) codeword norms, and checks that the runner-up lies more than 2*delta above the minimum,
+//            delta = 2^-20 (|z|^2 + max|e|^2 + 2 |z| max|e|) (tests/test_vq_two_phase_margin.py: then the minimum is
+//            the exhaustive search's argmin; true for > 99.9 % of the rows).  Any other row re-scores every codeword
+//            within 2*delta of its minimum with the oracle's exact arithmetic and tie rule (lowest index).
 // The result is identical to the exhaustive fp32 search by construction.
-// PERSISTENT: the heads of a row tile form a thread-block cluster (CTA = head) and a cluster walks the row tiles
-// t = blockIdx.x, blockIdx.x + gridDim.x, ...  Each CTA stages ITS head's codebook (hi / lo planes, exact norms) in
-// shared memory ONCE and keeps it for every tile (the one-tile-per-CTA form re-read 64 KB of codebook per 128 rows:
-// more L2 traffic than the rows themselves).  The commitment term's head sum goes through distributed shared memory
-// in head order, as in vq_search_cluster_kernel.
+// PERSISTENT + WARP-SPECIALISED: the heads of a row tile form a thread-block cluster (CTA = head) and a cluster walks
+// the row tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  Each CTA stages ITS head's codebook (hi / lo planes,
+// exact norms) in shared memory once.  See the kernel for the pipeline.
 #include "umma.cuh"
 #include <algorithm>
 #include <cooperative_groups.h>
@@ -29,77 +25,121 @@ namespace {
 
 constexpr int VU_ROWS = 128;                 // rows per CTA (TMEM lanes)
 constexpr int VU_DIM = 64;                   // dims per head (two K halves of 32)
-constexpr int VU_PRODUCERS = 256;            // 8 producer / epilogue warps
-constexpr int VU_THREADS = VU_PRODUCERS + 32;  // + the MMA warp
-constexpr int VU_MAX_CAND = 4;               // candidates kept per row half before the exhaustive fallback
-constexpr int VU_DV_LD = VU_DIM + 1;         // padded row pitch of the (q - z)^2 tile: a warp's 32 rows hit 32 banks
+constexpr int VU_EPI = 256;                  // warps 0-3 / 4-7: two epilogue groups (even / odd tiles of the CTA)
+constexpr int VU_STAGERS = 128;              // warps 8-9: operand staging, warps 10-11: head sum
+constexpr int VU_THREADS = VU_EPI + VU_STAGERS + 32;  // + the MMA warp
 
-// A and B planes use different shared-memory layouts, hence different descriptor high words; convergent predicated
-// issue (see umma_tf32_pred in umma.cuh)
-__device__ __forceinline__ void umma_tf32_kmaj_a_mnmaj_b_pred(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32,
-                                                              uint32_t idesc, uint32_t accumulate, uint32_t elected) {
+// ---- cluster / distributed-shared-memory helpers (the heads of a row tile exchange their commitment terms) ----
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+// fire-and-forget remote store that reports its 4 bytes to an mbarrier of the destination CTA (complete_tx): the
+// pusher needs no release fence (which would also wait for its global stores) and no arrival of its own
+__device__ __forceinline__ void st_async_f32(uint32_t cluster_addr, float v, uint32_t cluster_mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr),
+               "r"(__float_as_uint(v)), "r"(cluster_mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Wait for a barrier whose guarded data was written by OTHER CTAs of the cluster.  The probes are the plain
+// (CTA-scope) try_wait -- a cluster-scope acquire in the spin loop compiles to one CCTL.IVALL per probe, which kept
+// the L1 empty for every other warp of the SM, and a fence.acq_rel.cluster after it to a MEMBAR.ALL.GPU that also
+// drains this warp's own global stores -- followed by ONE cluster-scope acquiring test of the completed phase.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  mbar_wait(bar, parity);
   asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %7, 0;\n\t"
-      "mov.b64 da, {%1, %5};\n\t"
-      "mov.b64 db, {%2, %6};\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
-      :
-      : "r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "n"(DESC_HI_K), "n"(DESC_HI_MN),
-        "r"(elected)
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
       : "memory");
 }
+// tcgen05.ld without the wait, and a wait that names the destination registers (so no consumer of them can be
+// scheduled above it): lets the scan keep one TMEM load in flight under the compares of the previous chunk
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
-// the oracle's exact distance of row z (64 dims, registers) to codeword k of head codebook e (dim-major, ld = K)
-__device__ __forceinline__ float exact_dist(const float (&zr)[VU_DIM], float zz, const float* __restrict__ e, int K, int k,
-                                            float eek) {
-  float dot = 0.f;
+// one chunk of 16 approximate distances folded into FOUR independent (best, runner-up, index) accumulators (column
+// j goes to accumulator j & 3): with one epilogue warp per scheduler a single accumulator is a dependent chain of
+// ~30 cycles per column; four chains keep the scan issue-bound (~7 instructions per column).  Branch-free:
+//   second = min(second, max(best, d));  index = d < best ? c : index;  best = min(best, d)
+__device__ __forceinline__ void scan16(const uint32_t (&acc)[16], const float* __restrict__ ee, int c0, float zz,
+                                       float (&best)[4], float (&second)[4], int (&best_c)[4]) {
 #pragma unroll
-  for (int d = 0; d < VU_DIM; ++d) dot = fmaf(zr[d], __ldg(e + (size_t)d * K + k), dot);   // (zr stays in registers)
+  for (int j4 = 0; j4 < 16; j4 += 4) {
+    const float4 e4 = *reinterpret_cast<const float4*>(ee + c0 + j4);     // (same address in every lane: broadcast)
+    const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dj = (zz - 2.f * __uint_as_float(acc[j4 + j])) + ev[j];
+      second[j] = fminf(second[j], fmaxf(best[j], dj));
+      best_c[j] = dj < best[j] ? c0 + j4 + j : best_c[j];
+      best[j] = fminf(best[j], dj);
+    }
+  }
+}
+
+// v[i] = this lane's partial sum of row i  ->  returns the total of row `lane` (31 shuffles instead of 32 x 5)
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = upper ? v[i] : v[i + s];
+      const float keep = upper ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// the oracle's exact arithmetic for one (row, codeword): sequential fma over the dims, operands straight from global
+// memory (only the rare ambiguous rows come here)
+__device__ __noinline__ float exact_dist(const float* __restrict__ zrow, const float* __restrict__ e, int K, int k,
+                                         float eek) {
+  float zz = 0.f, dot = 0.f;
+  for (int d = 0; d < VU_DIM; ++d) {
+    const float zv = __ldg(zrow + d);
+    zz = fmaf(zv, zv, zz);
+    dot = fmaf(zv, __ldg(e + (size_t)d * K + k), dot);
+  }
   return (zz - 2.f * dot) + eek;
 }
 
-// exact fp32 codeword element (dim d, codeword k) from the resident operand planes: hi + lo is exact by construction
-template <int K>
-__device__ __forceinline__ float cb_elem(const uint8_t* __restrict__ sB, int d, int k) {
-  constexpr int B_PLANE = (K / 32) * 4096;
-  const int half = d >> 5, p = d & 31, c = k >> 2;
-  const uint8_t* a = sB + (half * 2) * B_PLANE + (uint32_t)(c >> 3) * 4096u + mn_off(p, c & 7) + (uint32_t)(k & 3) * 4u;
-  return *reinterpret_cast<const float*>(a) + *reinterpret_cast<const float*>(a + B_PLANE);
-}
-
-// dims D0 .. D0+31 of one row: gather the chosen codeword (from shared memory), write quant_raw / quant_st, leave
-// (q - z)^2 in `dv`
-template <int K, int D0>
-__device__ __forceinline__ void emit_row_half(const float (&zr)[VU_DIM], const uint8_t* __restrict__ sB, int k,
-                                              bool row_ok, int row, int r, int n_heads, int h,
-                                              float* __restrict__ quant_raw, float* __restrict__ quant_st,
-                                              float* __restrict__ dv) {
-  float q[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) q[j] = cb_elem<K>(sB, D0 + j, k);
-  if (row_ok) {
-    float* qr = quant_raw + (int64_t)row * (n_heads * VU_DIM) + h * VU_DIM + D0;
-    float* qs = quant_st + (int64_t)row * (n_heads * VU_DIM) + h * VU_DIM + D0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      *reinterpret_cast<float4*>(qr + j) = make_float4(q[j], q[j + 1], q[j + 2], q[j + 3]);
-      float4 st;
-      st.x = zr[D0 + j] + (q[j] - zr[D0 + j]);
-      st.y = zr[D0 + j + 1] + (q[j + 1] - zr[D0 + j + 1]);
-      st.z = zr[D0 + j + 2] + (q[j + 2] - zr[D0 + j + 2]);
-      st.w = zr[D0 + j + 3] + (q[j + 3] - zr[D0 + j + 3]);
-      *reinterpret_cast<float4*>(qs + j) = st;
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float dq = q[j] - zr[D0 + j];
-    dv[r * VU_DV_LD + D0 + j] = __fmul_rn(dq, dq);    // no fma contraction with the head sum
-  }
-}
-
+// Warp roles: warps 0-3 and 4-7 two epilogue groups (group g takes the CTA's tiles it = g, g + 2, ... and TMEM
+// accumulator buffer g, so two tiles are in flight per SM), warps 8-9 operand staging, warps 10-11 head sum, warp 12
+// MMA issue.
+// Pipeline per cluster (one CTA per head, every CTA walks the same row tiles t = blockIdx.x, + gridDim.x, ...):
+//   stagers   : A(t) -> shared memory (single stage, released by the tile's last MMA)            -> a_full
+//   MMA warp  : 24 tcgen05.mma into accumulator buffer t & 1 (2 x K TMEM columns)                -> a_free, acc_full[b]
+//   epilogue  : (lanes = dims) load its 32 rows coalesced, |z|^2 by warp reduction;
+//               (thread = row = TMEM lane) scan the K scores, pick the index                       -> acc_free[b]
+//               (lanes = dims) per row: codeword from the resident planes (one conflict-free 128-byte row per
+//               half and plane; hi + lo is the exact fp32 value), quant_raw / quant_st as full 128-byte lines,
+//               (q - z)^2 PUSHED into the inbox of the CTA that owns the row (rows [o*R, (o+1)*R) of a tile belong
+//               to CTA o, R = 128 / heads)                                                         -> inbox_full
+//   stagers   : (after staging tile t+1) sum the inbox over heads in head order, write diff       -> inbox_free
+// so the loads of tile t+1 and its MMAs run under the epilogue of tile t, every global access is a full line, and the
+// only cross-CTA traffic is 24 KB of fire-and-forget remote stores plus remote mbarrier arrivals -- no cluster-wide
+// barrier inside the loop.
 template <int K>   // codewords per head: 64, 128 or 256 (= the MMA's N)
 __global__ void __launch_bounds__(VU_THREADS, 1)
 vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __restrict__ embed,
@@ -109,159 +149,181 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int NB = K / 32;                     // 32-codeword blocks of the B operand
   constexpr int A_PLANE = VU_ROWS * 128;         // 16 KB: 128 rows x 32 dims
-  constexpr int B_PLANE = NB * 4096;             // NB blocks x 32 dims x 128 B
+  constexpr int B_PLANE = K * 128;               // K codewords x 32 dims
   // [half][plane]: half = dims 0..31 / 32..63, plane = hi / lo
   uint8_t* sA = smem;                                        // 4 x 16 KB
   uint8_t* sB = sA + 4 * A_PLANE;                            // 4 x B_PLANE
-  float* ee = reinterpret_cast<float*>(sB + 4 * B_PLANE);    // [K] exact |e_k|^2
-  float* row_best = ee + K;                                  // [2][128] per column half: best approximate distance
-  int* cand_cnt = reinterpret_cast<int*>(row_best + 2 * VU_ROWS);   // [2][128]
-  int* cand_idx = cand_cnt + 2 * VU_ROWS;                    // [2][128][VU_MAX_CAND]
-  int* row_idx = cand_idx + 2 * VU_ROWS * VU_MAX_CAND;       // [128] final index
-  float* ee_max = reinterpret_cast<float*>(row_idx + VU_ROWS);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ee_max + 2);
-  uint64_t* accum_bar = full_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-  float* dv = reinterpret_cast<float*>(sA);      // [128][65] per-row (q - z)^2 of this head; aliases A after the MMAs
+  float* inbox = reinterpret_cast<float*>(sB + 4 * B_PLANE); // [head][R rows][64 dims] : 32 KB
+  float* ee = inbox + VU_ROWS * VU_DIM;                      // [K] exact |e_k|^2
+  float* ee_max = ee + K;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ee_max + 2);
+  uint64_t* a_full = bars;            // count 2   (staging warps)
+  uint64_t* a_free = bars + 1;        // count 1   (tcgen05.commit)
+  uint64_t* acc_full = bars + 2;      // [2] count 1 (tcgen05.commit)
+  uint64_t* acc_free = bars + 4;      // [2] count 4 (epilogue warps)
+  uint64_t* inbox_full = bars + 6;    // count 1 (the owner's expect_tx) + 32 KB of st.async bytes per tile
+  uint64_t* inbox_free = bars + 7;    // [2] (tile parity) count n_heads (one remote arrival per owner CTA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_heads = gridDim.y, h = blockIdx.y;
+  const int lgR = 7 - (31 - __clz(n_heads));     // R = 128 / n_heads rows of a tile owned by each CTA (heads 1/2/4/8)
+  const int R = 1 << lgR;
   const int n_tiles = (n_rows + VU_ROWS - 1) / VU_ROWS;
   const float* e_h = embed + (size_t)h * VU_DIM * K;
-  constexpr int MMA_WARP = VU_PRODUCERS / 32;
+  constexpr int MMA_WARP = (VU_EPI + VU_STAGERS) / 32;
 
   if (tid == 0) {
-    mbar_init(full_bar, VU_PRODUCERS / 32);
-    mbar_init(accum_bar, 1);
+    mbar_init(a_full, 2);
+    mbar_init(a_free, 1);
+    mbar_init(acc_full, 1); mbar_init(acc_full + 1, 1);
+    mbar_init(acc_free, 4); mbar_init(acc_free + 1, 4);
+    mbar_init(inbox_full, 1);
+    mbar_arrive_expect_tx(inbox_full, VU_ROWS * VU_DIM * 4);     // tile 0: every head pushes its R rows x 64 dims
+    mbar_init(inbox_free, (uint32_t)n_heads); mbar_init(inbox_free + 1, (uint32_t)n_heads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)K)
+                 "r"((uint32_t)(2 * K))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-
-  if (warp < MMA_WARP) {
+  } else if (warp < VU_EPI / 32) {
     // ============ once per CTA: this head's codebook -> hi / lo operand planes, exact norms, max norm ============
-    // B: 64 dims x K/4 chunks of 4 consecutive codewords, read straight from the dim-major codebook
+    // lane = (codeword kk of a block of 8, one of 4 sixteen-byte dim chunks): the global reads are full 32-byte
+    // sectors along the codewords of one dim (the codebook is dim-major), the 16-byte shared-memory stores of a
+    // quarter warp hit the 8 distinct chunk positions c ^ (k & 7) of 8 consecutive rows: conflict-free
+    {
+      const int kk = lane & 7, dc = lane >> 3;
 #pragma unroll 4
-    for (int i = 0; i < (VU_DIM * (K / 4)) / VU_PRODUCERS; ++i) {
-      const int e = tid + VU_PRODUCERS * i;
-      const int d_ = e / (K / 4), c = e - d_ * (K / 4);
-      const int half = d_ >> 5, p = d_ & 31, nblk = c >> 3, c16 = c & 7;
-      const float4 x = __ldg(reinterpret_cast<const float4*>(e_h + (size_t)d_ * K + c * 4));
-      const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-      uint8_t* d = sB + (half * 2) * B_PLANE + (uint32_t)nblk * 4096u + mn_off(p, c16);
-      *reinterpret_cast<float4*>(d) = hi;
-      *reinterpret_cast<float4*>(d + B_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+      for (int item = warp; item < (K / 8) * 4; item += VU_EPI / 32) {
+        const int k = (item >> 2) * 8 + kk, c = (item & 3) * 4 + dc;      // codeword, 16-byte chunk of its 64 dims
+        float xv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xv[j] = __ldg(e_h + (size_t)(c * 4 + j) * K + k);
+        const float4 hi = make_float4(tf32_hi(xv[0]), tf32_hi(xv[1]), tf32_hi(xv[2]), tf32_hi(xv[3]));
+        uint8_t* d = sB + ((c >> 3) * 2) * B_PLANE + (uint32_t)k * 128u + (uint32_t)((((c & 7) ^ k) & 7) << 4);
+        *reinterpret_cast<float4*>(d) = hi;
+        *reinterpret_cast<float4*>(d + B_PLANE) = make_float4(xv[0] - hi.x, xv[1] - hi.y, xv[2] - hi.z, xv[3] - hi.w);
+      }
     }
-    // exact codeword norms, the oracle's order (sequential fma over d)
-    for (int k = tid; k < K; k += VU_PRODUCERS) {
-      float s = 0.f;
-#pragma unroll 8
-      for (int d_ = 0; d_ < VU_DIM; ++d_) { const float v = __ldg(e_h + (size_t)d_ * K + k); s = fmaf(v, v, s); }
-      ee[k] = s;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the planes are read by the async proxy (MMA)
+    asm volatile("bar.sync 1, %0;" ::"n"(VU_EPI) : "memory");
+    // exact codeword norms in the oracle's order (sequential fma over d), from the resident planes: hi + lo is the
+    // exact fp32 element
+    for (int k = tid; k < K; k += VU_EPI) {
+      float sq = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const uint8_t* a = sB + ((c >> 3) * 2) * B_PLANE + (uint32_t)k * 128u + (uint32_t)((((c & 7) ^ k) & 7) << 4);
+        const float4 hi = *reinterpret_cast<const float4*>(a);
+        const float4 lo = *reinterpret_cast<const float4*>(a + B_PLANE);
+        float v;
+        v = hi.x + lo.x; sq = fmaf(v, v, sq);
+        v = hi.y + lo.y; sq = fmaf(v, v, sq);
+        v = hi.z + lo.z; sq = fmaf(v, v, sq);
+        v = hi.w + lo.w; sq = fmaf(v, v, sq);
+      }
+      ee[k] = sq;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(VU_PRODUCERS) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(VU_EPI) : "memory");
     if (warp == 0) {
       float m = 0.f;
       for (int k = lane; k < K; k += 32) m = fmaxf(m, ee[k]);
       m = warp_max(m);
       if (lane == 0) ee_max[0] = m;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(VU_PRODUCERS) : "memory");      // ee_max visible
   }
+  tc_fence_before();
+  __syncthreads();
+  cluster.sync();         // every CTA's barriers are initialised before any remote arrival / store targets them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
   const float inv_heads = 1.f / (float)n_heads;
-  const uint32_t elected = elect_one();
 
-  uint32_t par = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1u) {
-  const int row0 = tile * VU_ROWS;
-  if (warp < MMA_WARP) {
-    // ================================ operand staging: this tile's rows ================================
-    // A: 128 rows x 16 sixteen-byte chunks; consecutive threads read consecutive chunks of a row (256 B per row)
-#pragma unroll
-    for (int i = 0; i < (VU_ROWS * 16) / VU_PRODUCERS; ++i) {
-      const int e = tid + VU_PRODUCERS * i;
-      const int r = e >> 4, c_all = e & 15;
-      const int half = c_all >> 3, chunk = c_all & 7;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + r < n_rows)
-        x = __ldg(reinterpret_cast<const float4*>(z + (int64_t)(row0 + r) * ld_z + h * VU_DIM + c_all * 4));
-      const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-      uint8_t* d = sA + (half * 2) * A_PLANE + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
-                   (uint32_t)((chunk ^ (r & 7)) << 4);
-      *reinterpret_cast<float4*>(d) = hi;
-      *reinterpret_cast<float4*>(d + A_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
-    }
-    publish_and_arrive_warp(full_bar);      // (on the first tile this also publishes the codebook planes)
-
-    // ================================ phase 2: one thread per (row, column half) ================================
-    const int lane_grp = warp & 3, chalf = warp >> 2;
-    const int r = lane_grp * 32 + lane;                 // TMEM lane = row inside the tile
-    const int row = row0 + r;
-    const bool row_ok = row < n_rows;
-    const float* zrow = z + (int64_t)(row_ok ? row : (n_rows - 1)) * ld_z + h * VU_DIM;
-    float zr[VU_DIM];
-#pragma unroll
-    for (int d_ = 0; d_ < VU_DIM; d_ += 4) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(zrow + d_));
-      zr[d_] = t.x; zr[d_ + 1] = t.y; zr[d_ + 2] = t.z; zr[d_ + 3] = t.w;
-    }
-    float zz = 0.f;
-#pragma unroll
-    for (int d_ = 0; d_ < VU_DIM; ++d_) zz = fmaf(zr[d_], zr[d_], zz);
+  if (warp < VU_EPI / 32) {
+    // ================================================ epilogue ================================================
+    const int grp = warp >> 2, quad = warp & 3;          // TMEM lanes 32 * quad .. + 31 (a warp reaches quadrant warp % 4)
+    const uint32_t taddr_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)grp * (uint32_t)K;
+    const uint8_t* sBl = sB + (uint32_t)(lane & 3) * 4u;
+    const int lx = lane >> 2;
     const float emax = ee_max[0];
-    const float delta2 = 2.f * 9.5367431640625e-07f * (zz + emax + 2.f * sqrtf(zz * emax));   // 2 * 2^-20 * (|z| + |e|)^2
-
-    mbar_wait(accum_bar, par);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-    constexpr int CH = K / 2;                           // columns per thread
-    const int cbeg = chalf * CH;
-    // ONE pass over this thread's K/2 columns: smallest approximate distance (lowest index on ties), its index, and
-    // the second smallest value.  A row whose runner-up (over both halves) lies more than 2*delta above its best has a
-    // single candidate -- the exhaustive fp32 search's argmin (tests/test_vq_two_phase_margin.py); any other row is
-    // re-scored exactly over all K codewords (< 0.1 % of the rows).
-    float best = INFINITY, second = INFINITY;
-    int best_c = 0x7fffffff;
-#pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + CH; c0 += 16) {
-      float acc[16];
-      tmem_ld16(taddr + (uint32_t)c0, acc);
+    const int wr0 = quad * 32;                           // first tile row of this warp
+    const int64_t row_pitch = (int64_t)n_heads * VU_DIM;
+    // the inbox slots of this warp's rows: rows 0-15 and 16-31 (different owners only at 8 heads, R = 16)
+    const uint32_t inbox_addr = smem_u32(inbox), full_addr = smem_u32(inbox_full);
+    const uint32_t dst_a = map_to_cta(inbox_addr + (uint32_t)(((h << lgR) + (wr0 & (R - 1))) * VU_DIM + lane) * 4u,
+                                      (uint32_t)(wr0 >> lgR));
+    const uint32_t dst_b = map_to_cta(inbox_addr + (uint32_t)(((h << lgR) + ((wr0 + 16) & (R - 1))) * VU_DIM + lane) * 4u,
+                                      (uint32_t)((wr0 + 16) >> lgR));
+    const uint32_t full_a = map_to_cta(full_addr, (uint32_t)(wr0 >> lgR));
+    const uint32_t full_b = map_to_cta(full_addr, (uint32_t)((wr0 + 16) >> lgR));
+    uint32_t it = (uint32_t)grp;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int row_w = tile * VU_ROWS + wr0;            // global row of this warp's first row
+      // ---- lanes = dims: the warp's 32 rows as full 128-byte lines; |z|^2 of row i lands in lane i
+      float z0[32], z1[32];
+      {
+        const float* zp = z + (int64_t)row_w * ld_z + h * VU_DIM + lane;
+        const int last = n_rows - 1 - row_w;             // rows past the end re-read the last row (never stored)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float dj = (zz - 2.f * acc[j]) + ee[c0 + j];
-        if (dj < best) { second = best; best = dj; best_c = c0 + j; }
-        else second = fminf(second, dj);
+        for (int i = 0; i < 32; ++i) {
+          const float* zi = zp + (int64_t)min(i, last) * ld_z;
+          z0[i] = __ldg(zi);
+          z1[i] = __ldg(zi + 32);
+        }
       }
-    }
-    row_best[chalf * VU_ROWS + r] = best;
-    cand_cnt[chalf * VU_ROWS + r] = best_c;
-    reinterpret_cast<float*>(cand_idx)[chalf * VU_ROWS + r] = second;
-    asm volatile("bar.sync 1, %0;" ::"n"(VU_PRODUCERS) : "memory");
+      float zz;
+      {
+        float part[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) part[i] = fmaf(z1[i], z1[i], z0[i] * z0[i]);
+        zz = warp_transpose_reduce32(part, lane);
+      }
+      const float delta2 = 2.f * 9.5367431640625e-07f * (zz + emax + 2.f * sqrtf(zz * emax));   // 2 * 2^-20 * (|z| + |e|)^2
 
-    if (chalf == 0) {                                    // (warp-uniform) the row's owner merges the two halves
-      const float b0 = row_best[r], b1 = row_best[VU_ROWS + r];
-      const float s0 = reinterpret_cast<const float*>(cand_idx)[r], s1 = reinterpret_cast<const float*>(cand_idx)[VU_ROWS + r];
-      const int k0 = cand_cnt[r], k1 = cand_cnt[VU_ROWS + r];
-      const bool lo_wins = b0 <= b1;                     // ties: the lower half holds the lower indices
-      const float bmin = lo_wins ? b0 : b1;
-      const float runner = fminf(lo_wins ? b1 : b0, fminf(s0, s1));
-      int best_k = lo_wins ? k0 : k1;
-      const bool amb = !(runner > bmin + delta2) || (unsigned)best_k >= (unsigned)K;
+      // ---- thread = row: one pass over the K scores (accumulator buffer = group)
+      mbar_wait(acc_full + grp, (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = taddr_lane;
+      float best, second;
+      int best_k;
+      {
+        float b4[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, s4[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+        int k4[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+        uint32_t acc0[16], acc1[16];
+        tmem_ld16_issue(taddr, acc0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < K; c0 += 32) {
+          tmem_ld_wait16(acc0);
+          tmem_ld16_issue(taddr + (uint32_t)(c0 + 16), acc1);
+          scan16(acc0, ee, c0, zz, b4, s4, k4);
+          tmem_ld_wait16(acc1);
+          if (c0 + 32 < K) tmem_ld16_issue(taddr + (uint32_t)(c0 + 32), acc0);
+          scan16(acc1, ee, c0 + 16, zz, b4, s4, k4);
+        }
+        // merge: the overall minimum, its index, and the smallest value that is not the winner's.  (An exact tie
+        // between accumulators leaves second == best: the row is ambiguous and the exact pass below applies the
+        // lowest-index rule.)
+        best = b4[0]; second = s4[0]; best_k = k4[0];
+#pragma unroll
+        for (int a = 1; a < 4; ++a) {
+          const bool wins = b4[a] < best;
+          second = fminf(fminf(second, s4[a]), wins ? best : b4[a]);
+          best_k = wins ? k4[a] : best_k;
+          best = wins ? b4[a] : best;
+        }
+      }
+      // A row whose runner-up lies more than 2*delta above its best has a single candidate -- the exhaustive fp32
+      // search's argmin (tests/test_vq_two_phase_margin.py); any other row is re-scored exactly.
+      const bool amb = !(second > best + delta2) || (unsigned)best_k >= (unsigned)K;
       if (__any_sync(0xffffffffu, amb)) {
         // some row of this warp is ambiguous (or NaN / Inf): the warp re-reads its rows' K dot products
         // (tcgen05.ld is warp-collective) and the ambiguous lanes re-score every codeword within 2*delta of their
         // minimum with the oracle's exact arithmetic, in ascending index order (lowest index wins ties)
-        const float thr = bmin + delta2;
+        const float thr = best + delta2;
+        const float* zrow = z + (int64_t)min(row_w + lane, n_rows - 1) * ld_z + h * VU_DIM;
         float bd = INFINITY;
         int bk = 0x7fffffff;
 #pragma unroll 1
@@ -269,10 +331,10 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
           float acc[16];
           tmem_ld16(taddr + (uint32_t)c0, acc);
           if (amb) {
-#pragma unroll 1
+#pragma unroll
             for (int j = 0; j < 16; ++j) {
               if ((zz - 2.f * acc[j]) + ee[c0 + j] <= thr) {
-                const float dk = exact_dist(zr, zz, e_h, K, c0 + j, ee[c0 + j]);
+                const float dk = exact_dist(zrow, e_h, K, c0 + j, ee[c0 + j]);
                 if (dk < bd) { bd = dk; bk = c0 + j; }
               }
             }
@@ -280,74 +342,178 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
         }
         if (amb) best_k = ((unsigned)bk < (unsigned)K) ? bk : 0;     // no candidate at all (NaN row): index 0
       }
-      row_idx[r] = best_k;
-      if (row_ok) idx[(int64_t)row * n_heads + h] = (int64_t)best_k;
-    }
-    tc_fence_before();                                   // this thread's TMEM reads of the tile are complete
-    asm volatile("bar.sync 1, %0;" ::"n"(VU_PRODUCERS) : "memory");
-    // gather, straight-through output and per-row squares: the two threads of a row take 32 dims each.
-    // (dv aliases the A operand: every MMA that read it has completed -- accum_bar -- and all threads are past it)
-    // (sB is never overwritten; dv aliases sA, so the codeword is gathered into registers BEFORE dv is written --
-    //  emit_row_half reads sB only)
-    if (chalf == 0)
-      emit_row_half<K, 0>(zr, sB, row_idx[r], row_ok, row, r, n_heads, h, quant_raw, quant_st, dv);
-    else
-      emit_row_half<K, 32>(zr, sB, row_idx[r], row_ok, row, r, n_heads, h, quant_raw, quant_st, dv);
-  } else {
-    // ================================ MMA issuer (convergent, predicated issue) ================================
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) |      // D f32, A/B tf32, B MN-major
-                               ((uint32_t)(K >> 3) << 17) | ((uint32_t)(VU_ROWS >> 4) << 24);
-    mbar_wait(full_bar, par);
-    tc_fence_after();
-    const uint32_t a0 = desc_lo_k(smem_u32(sA)), b0 = desc_lo_mn(smem_u32(sB));
+      tc_fence_before();                                   // this thread's TMEM reads of the tile are complete
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free + grp);
+      if (row_w + lane < n_rows) idx[(int64_t)(row_w + lane) * n_heads + h] = (int64_t)best_k;
+      // the owners have summed the previous tile (the other group's): the inboxes may be overwritten.  The owners
+      // signal tile t on inbox_free[t & 1], so each group watches ONE barrier and sees every one of its phases (with
+      // a single barrier a group could be 0, 1 or 2 phases behind, which a parity wait cannot tell apart).
+      if (it > 0) mbar_wait_cluster(inbox_free + ((it - 1) & 1u), ((it - 1) >> 1) & 1u);
+      // ---- lanes = dims, four rows in flight: codeword k (dims lane, 32 + lane: one 128-byte row per half and
+      //      plane, 16-byte chunks XORed with k & 7).  Pass 1 pushes (q - z)^2 to the rows' owners -- that is what
+      //      the other CTAs wait for --, pass 2 gathers again and writes quant_raw / quant_st as full lines.
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const uint32_t ad = a0 + (uint32_t)(half * 2) * (A_PLANE >> 4);
-      const uint32_t bd = b0 + (uint32_t)(half * 2) * (B_PLANE >> 4);
+      for (int i0 = 0; i0 < 32; i0 += 4) {
+        float q0[4], q1[4];
 #pragma unroll
-      for (int kg = 0; kg < 4; ++kg) {
-        // 8 dims per MMA: A advances 32 B along its 128-byte rows (2 units), B two 4-row atoms (1 KB = 64 units)
-        const uint32_t a_hi = ad + 2 * kg, b_hi = bd + 64 * kg;
-        const uint32_t a_lo = a_hi + (A_PLANE >> 4), b_lo = b_hi + (B_PLANE >> 4);
-        umma_tf32_kmaj_a_mnmaj_b_pred(tmem_base, a_lo, b_hi, IDESC, (half > 0 || kg > 0) ? 1u : 0u, elected);
-        umma_tf32_kmaj_a_mnmaj_b_pred(tmem_base, a_hi, b_lo, IDESC, 1u, elected);
-        umma_tf32_kmaj_a_mnmaj_b_pred(tmem_base, a_hi, b_hi, IDESC, 1u, elected);
+        for (int j = 0; j < 4; ++j) {
+          const int k = __shfl_sync(0xffffffffu, best_k, i0 + j);
+          const uint8_t* a = sBl + (uint32_t)k * 128u + (uint32_t)(((lx ^ k) & 7) << 4);
+          q0[j] = *reinterpret_cast<const float*>(a) + *reinterpret_cast<const float*>(a + B_PLANE);
+          q1[j] = *reinterpret_cast<const float*>(a + 2 * B_PLANE) + *reinterpret_cast<const float*>(a + 3 * B_PLANE);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j;
+          const float dq0 = q0[j] - z0[i], dq1 = q1[j] - z1[i];
+          const uint32_t dst = (i < 16 ? dst_a + (uint32_t)i * 256u : dst_b + (uint32_t)(i - 16) * 256u);
+          const uint32_t bar = (i < 16 ? full_a : full_b);
+          st_async_f32(dst, __fmul_rn(dq0, dq0), bar);       // no fma contraction with the head sum
+          st_async_f32(dst + 128u, __fmul_rn(dq1, dq1), bar);
+        }
+      }
+      float* qr = quant_raw + (int64_t)row_w * row_pitch + h * VU_DIM + lane;
+      float* qs = quant_st + (int64_t)row_w * row_pitch + h * VU_DIM + lane;
+      const int n_ok = n_rows - row_w;                     // rows i < n_ok exist
+#pragma unroll
+      for (int i0 = 0; i0 < 32; i0 += 4) {
+        float q0[4], q1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = __shfl_sync(0xffffffffu, best_k, i0 + j);
+          const uint8_t* a = sBl + (uint32_t)k * 128u + (uint32_t)(((lx ^ k) & 7) << 4);
+          q0[j] = *reinterpret_cast<const float*>(a) + *reinterpret_cast<const float*>(a + B_PLANE);
+          q1[j] = *reinterpret_cast<const float*>(a + 2 * B_PLANE) + *reinterpret_cast<const float*>(a + 3 * B_PLANE);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j;
+          if (i < n_ok) {                                    // (warp-uniform)
+            qr[0] = q0[j];
+            qr[32] = q1[j];
+            qs[0] = z0[i] + (q0[j] - z0[i]);
+            qs[32] = z1[i] + (q1[j] - z1[i]);
+          }
+          qr += row_pitch;
+          qs += row_pitch;
+        }
       }
     }
-    umma_commit_pred(accum_bar, elected);
-    __syncwarp();
+  } else if (warp < VU_EPI / 32 + 2) {
+    // ============================= operand staging (A): runs ahead, gated by a_free =============================
+    const int st = tid - VU_EPI;                         // 0..63
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int row0 = tile * VU_ROWS;
+      if (it > 0) mbar_wait(a_free, (it - 1) & 1u);        // the previous tile's MMAs have read the stage
+      // A: 128 rows x 16 sixteen-byte chunks; consecutive threads read consecutive chunks of a row (256 B per row)
+#pragma unroll 8
+      for (int i = 0; i < (VU_ROWS * 16) / 64; ++i) {
+        const int e = st + 64 * i;
+        const int r = e >> 4, c_all = e & 15;
+        const int half = c_all >> 3, chunk = c_all & 7;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < n_rows)
+          x = __ldg(reinterpret_cast<const float4*>(z + (int64_t)(row0 + r) * ld_z + h * VU_DIM + c_all * 4));
+        const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+        uint8_t* d = sA + (half * 2) * A_PLANE + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+                     (uint32_t)((chunk ^ (r & 7)) << 4);
+        *reinterpret_cast<float4*>(d) = hi;
+        *reinterpret_cast<float4*>(d + A_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+      }
+      publish_and_arrive_warp(a_full);
+    }
+  } else if (warp < MMA_WARP) {
+    // ================================ head sum of the commitment term ================================
+    // this CTA owns rows [h*R, (h+1)*R) of every tile: sum the heads in head order, scale, write diff
+    const int st = tid - VU_EPI - 64;                    // 0..63
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int row0 = tile * VU_ROWS;
+      mbar_wait_cluster(inbox_full, it & 1u);
+      if (st == 0) mbar_arrive_expect_tx(inbox_full, VU_ROWS * VU_DIM * 4);    // the next tile's bytes
+      auto sum_item = [&](int e) {
+        const int lr = e >> 4, d4 = e & 15;
+        float4 a = *reinterpret_cast<const float4*>(inbox + (size_t)lr * VU_DIM + d4 * 4);
+        for (int hh = 1; hh < n_heads; ++hh) {
+          const float4 v = *reinterpret_cast<const float4*>(inbox + ((size_t)(hh << lgR) + lr) * VU_DIM + d4 * 4);
+          a.x = __fadd_rn(a.x, v.x); a.y = __fadd_rn(a.y, v.y);
+          a.z = __fadd_rn(a.z, v.z); a.w = __fadd_rn(a.w, v.w);
+        }
+        return make_float4(a.x * inv_heads, a.y * inv_heads, a.z * inv_heads, a.w * inv_heads);
+      };
+      auto store_item = [&](int e, const float4& v) {
+        const int row = row0 + (h << lgR) + (e >> 4);
+        if (row < n_rows) *reinterpret_cast<float4*>(diff + (int64_t)row * VU_DIM + (e & 15) * 4) = v;
+      };
+      if (R <= 32) {
+        // (>= 4 heads) the sums wait in registers: the inbox is handed back before the global stores are issued
+        float4 acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (st + 64 * u < R * 16) acc[u] = sum_item(st + 64 * u);
+        asm volatile("bar.sync 2, 64;" ::: "memory");      // both warps hold their sums: the inbox is free
+        if (st < n_heads) mbar_arrive_remote_release(map_to_cta(smem_u32(inbox_free + (it & 1u)), (uint32_t)st));
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (st + 64 * u < R * 16) store_item(st + 64 * u, acc[u]);
+      } else {
+        for (int e = st; e < R * 16; e += 64) store_item(e, sum_item(e));
+        asm volatile("bar.sync 2, 64;" ::: "memory");
+        if (st < n_heads) mbar_arrive_remote_release(map_to_cta(smem_u32(inbox_free + (it & 1u)), (uint32_t)st));
+      }
+    }
+  } else {
+    // ================================ MMA issuer (convergent, predicated issue) ================================
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) |                    // D f32, A/B tf32, both K-major
+                               ((uint32_t)(K >> 3) << 17) | ((uint32_t)(VU_ROWS >> 4) << 24);
+    const uint32_t elected = elect_one();
+    const uint32_t a0 = desc_lo_k(smem_u32(sA)), b0 = desc_lo_k(smem_u32(sB));
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t b = it & 1u;
+      if (it >= 2) mbar_wait(acc_free + b, ((it >> 1) - 1u) & 1u);   // epilogue group b has drained its accumulator
+      mbar_wait(a_full, it & 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + b * (uint32_t)K;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t ad = a0 + (uint32_t)(half * 2) * (A_PLANE >> 4);
+        const uint32_t bd = b0 + (uint32_t)(half * 2) * (B_PLANE >> 4);
+#pragma unroll
+        for (int kg = 0; kg < 4; ++kg) {
+          // 8 dims per MMA: both operands advance 32 B along their 128-byte rows (2 descriptor units)
+          const uint32_t a_hi = ad + 2 * kg, b_hi = bd + 2 * kg;
+          const uint32_t a_lo = a_hi + (A_PLANE >> 4), b_lo = b_hi + (B_PLANE >> 4);
+          umma_tf32_pred<DESC_HI_K>(tmem_d, a_lo, b_hi, IDESC, (half > 0 || kg > 0) ? 1u : 0u, elected);
+          umma_tf32_pred<DESC_HI_K>(tmem_d, a_hi, b_lo, IDESC, 1u, elected);
+          umma_tf32_pred<DESC_HI_K>(tmem_d, a_hi, b_hi, IDESC, 1u, elected);
+        }
+      }
+      umma_commit_pred(a_free, elected);
+      umma_commit_pred(acc_full + b, elected);
+      __syncwarp();
+    }
   }
-  // head sum of the commitment term in head order through distributed shared memory (cluster = the heads of this tile)
+  // nobody exits (or frees its TMEM) while a neighbour may still push into its inbox / arrive on its barriers
+  tc_fence_before();
   __syncthreads();
   cluster.sync();
-  const int rows_here = min(VU_ROWS, n_rows - row0);
-  // this CTA combines the rows ri = h, h + n_heads, ...
-  const int my_rows = (rows_here - h + n_heads - 1) / n_heads;
-  for (int e = tid; e < my_rows * VU_DIM; e += VU_THREADS) {
-    const int ri = (e >> 6) * n_heads + h, d_ = e & (VU_DIM - 1);
-    float acc = *cluster.map_shared_rank(dv + ri * VU_DV_LD + d_, 0);
-    for (int hh = 1; hh < n_heads; ++hh) acc = __fadd_rn(acc, *cluster.map_shared_rank(dv + ri * VU_DV_LD + d_, hh));
-    diff[(int64_t)(row0 + ri) * VU_DIM + d_] = acc * inv_heads;
-  }
-  cluster.sync();     // nobody overwrites its tile (next A staging) or exits while a neighbour may still read it
-  }   // tile loop
-  __syncthreads();
   if (warp == MMA_WARP) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)K) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * K))
+                 : "memory");
   }
 }
 
 template <int K>
 int launch_vq_umma(const float* z, int64_t ld_z, const float* embed, float* quant_raw, float* quant_st, float* diff,
                    int64_t* idx, int n_rows, int n_heads, cudaStream_t st) {
-  constexpr int NB = K / 32;
-  const size_t smem = 1024 + 4 * (size_t)VU_ROWS * 128 + 4 * (size_t)NB * 4096 + (size_t)K * 4 +
-                      2 * VU_ROWS * 4 + 2 * VU_ROWS * 4 + 2 * VU_ROWS * VU_MAX_CAND * 4 + VU_ROWS * 4 + 8 + 16 + 16;
+  const size_t smem = 1024 + 4 * (size_t)VU_ROWS * 128 + 4 * (size_t)K * 128 + (size_t)VU_ROWS * VU_DIM * 4 +
+                      (size_t)K * 4 + 8 + 8 * 8 + 16;
+  static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // per n_heads: co-resident clusters of this kernel
   cudaLaunchConfig_t cfg = {};
-  // persistent: one cluster (n_heads CTAs, one per SM) per slot, each walking its share of the row tiles
-  const int n_clusters = std::max(1, std::min(ceil_div(n_rows, VU_ROWS), num_sms() / n_heads));
-  cfg.gridDim = dim3((unsigned)n_clusters, (unsigned)n_heads, 1);
   cfg.blockDim = dim3(VU_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -358,9 +524,22 @@ int launch_vq_umma(const float* z, int64_t ld_z, const float* embed, float* quan
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cudaFuncSetAttribute(vq_search_umma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-      cudaSuccess)
-    return MSMC_ERR_LAUNCH;
+  if (max_clusters[n_heads] == 0) {
+    if (cudaFuncSetAttribute(vq_search_umma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return MSMC_ERR_LAUNCH;
+    // persistent: the grid must not exceed what is co-resident (clusters are placed inside one GPC, so this can be
+    // fewer than num_sms / n_heads); a cluster left for a second wave would double the kernel's duration
+    cfg.gridDim = dim3((unsigned)(num_sms() / n_heads), (unsigned)n_heads, 1);
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, vq_search_umma_kernel<K>, &cfg) != cudaSuccess || nc <= 0) {
+      cudaGetLastError();
+      nc = std::max(1, num_sms() / n_heads - 2);
+    }
+    max_clusters[n_heads] = std::min(nc, num_sms() / n_heads);
+  }
+  const int n_clusters = std::max(1, std::min(ceil_div(n_rows, VU_ROWS), max_clusters[n_heads]));
+  cfg.gridDim = dim3((unsigned)n_clusters, (unsigned)n_heads, 1);
   if (cudaLaunchKernelEx(&cfg, vq_search_umma_kernel<K>, z, ld_z, embed, quant_raw, quant_st, diff, idx, n_rows) !=
       cudaSuccess)
     return MSMC_ERR_LAUNCH;
@@ -377,6 +556,7 @@ extern "C" int msmc_vq_search_umma(const float* z, int64_t ld_z, const float* em
                                    int32_t dim, int32_t n_embed, void* stream) {
   MSMC_REQUIRE(z && embed && quant_raw && quant_st && diff && idx);
   MSMC_REQUIRE(n_rows > 0 && n_heads > 0 && n_heads <= 8);
+  if (n_heads != 1 && n_heads != 2 && n_heads != 4 && n_heads != 8) return MSMC_ERR_UNSUPPORTED;
   if (dim != VU_DIM || (n_embed != 64 && n_embed != 128 && n_embed != 256)) return MSMC_ERR_UNSUPPORTED;
   MSMC_REQUIRE((ld_z & 3) == 0 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(embed) |
                                     reinterpret_cast<uintptr_t>(quant_raw) | reinterpret_cast<uintptr_t>(quant_st)) & 15) == 0);

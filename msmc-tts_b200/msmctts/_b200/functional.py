@@ -640,7 +640,7 @@ class _VQFn(torch.autograd.Function):
         diff = torch.empty((n_rows, dim), dtype=torch.float32, device=z.device)
         idx = torch.empty((n_rows, n_heads), dtype=torch.int64, device=z.device)
         entry = "msmc_vq_search"
-        if VQ_UMMA and dim == 64 and K in (64, 128, 256) and n_heads <= 8 and z2.stride(0) % 4 == 0 \
+        if VQ_UMMA and dim == 64 and K in (64, 128, 256) and n_heads in (1, 2, 4, 8) and z2.stride(0) % 4 == 0 \
                 and z2.data_ptr() % 16 == 0:
             entry = "msmc_vq_search_umma"      # experimental two-phase tensor-core search (default off)
         L.call(entry, L.ptr(z2), C.c_int64(z2.stride(0)), L.ptr(embed), L.ptr(q_raw), L.ptr(q_st),
