@@ -476,7 +476,9 @@ def build_gpu_trainer(cfg, device, distributed, rank, world, use_graph=False, re
 def vq_bandwidth(device, pk, K=K_CODEWORDS):
     """VQ search kernel alone: at-config (both stages of one forward: N = 3840 + 960 rows) and an N sweep."""
     from msmctts._b200 import functional as Fn
-    out = {"codewords_per_head": K}
+    out = {"codewords_per_head": K,
+           "kernel": "two-phase tcgen05 search (vq_search_umma_kernel) from %d rows on, CUDA-core cluster kernel "
+                     "below (MSMC_VQ_UMMA=%s); identical results" % (Fn.VQ_UMMA_MIN_ROWS, Fn.VQ_UMMA)}
     heads, dim = 4, 64
     embed = torch.randn(heads, dim, K, device=device)
 

@@ -184,6 +184,27 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
     mbar_init(inbox_free, (uint32_t)n_heads); mbar_init(inbox_free + 1, (uint32_t)n_heads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();        // barriers initialised: the staging warps may signal a_full during the prologue
+  // A operand of one tile: 128 rows x 16 sixteen-byte chunks; consecutive threads read consecutive chunks of a row
+  // (256 B per row); hi / lo planes, K-major SWIZZLE_128B
+  auto stage_tile = [&](int tile, int st) {
+    const int row0 = tile * VU_ROWS;
+#pragma unroll 8
+    for (int i = 0; i < (VU_ROWS * 16) / 64; ++i) {
+      const int e = st + 64 * i;
+      const int r = e >> 4, c_all = e & 15;
+      const int half = c_all >> 3, chunk = c_all & 7;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + r < n_rows)
+        x = __ldg(reinterpret_cast<const float4*>(z + (int64_t)(row0 + r) * ld_z + h * VU_DIM + c_all * 4));
+      const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+      uint8_t* d = sA + (half * 2) * A_PLANE + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+                   (uint32_t)((chunk ^ (r & 7)) << 4);
+      *reinterpret_cast<float4*>(d) = hi;
+      *reinterpret_cast<float4*>(d + A_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+    }
+    publish_and_arrive_warp(a_full);
+  };
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)(2 * K))
@@ -234,6 +255,8 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
       m = warp_max(m);
       if (lane == 0) ee_max[0] = m;
     }
+  } else if (warp < VU_EPI / 32 + 2) {
+    stage_tile(blockIdx.x, tid - VU_EPI);      // the first tile's rows arrive while the codebook is being staged
   }
   tc_fence_before();
   __syncthreads();
@@ -346,33 +369,9 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_free + grp);
       if (row_w + lane < n_rows) idx[(int64_t)(row_w + lane) * n_heads + h] = (int64_t)best_k;
-      // the owners have summed the previous tile (the other group's): the inboxes may be overwritten.  The owners
-      // signal tile t on inbox_free[t & 1], so each group watches ONE barrier and sees every one of its phases (with
-      // a single barrier a group could be 0, 1 or 2 phases behind, which a parity wait cannot tell apart).
-      if (it > 0) mbar_wait_cluster(inbox_free + ((it - 1) & 1u), ((it - 1) >> 1) & 1u);
       // ---- lanes = dims, four rows in flight: codeword k (dims lane, 32 + lane: one 128-byte row per half and
-      //      plane, 16-byte chunks XORed with k & 7).  Pass 1 pushes (q - z)^2 to the rows' owners -- that is what
-      //      the other CTAs wait for --, pass 2 gathers again and writes quant_raw / quant_st as full lines.
-#pragma unroll
-      for (int i0 = 0; i0 < 32; i0 += 4) {
-        float q0[4], q1[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = __shfl_sync(0xffffffffu, best_k, i0 + j);
-          const uint8_t* a = sBl + (uint32_t)k * 128u + (uint32_t)(((lx ^ k) & 7) << 4);
-          q0[j] = *reinterpret_cast<const float*>(a) + *reinterpret_cast<const float*>(a + B_PLANE);
-          q1[j] = *reinterpret_cast<const float*>(a + 2 * B_PLANE) + *reinterpret_cast<const float*>(a + 3 * B_PLANE);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = i0 + j;
-          const float dq0 = q0[j] - z0[i], dq1 = q1[j] - z1[i];
-          const uint32_t dst = (i < 16 ? dst_a + (uint32_t)i * 256u : dst_b + (uint32_t)(i - 16) * 256u);
-          const uint32_t bar = (i < 16 ? full_a : full_b);
-          st_async_f32(dst, __fmul_rn(dq0, dq0), bar);       // no fma contraction with the head sum
-          st_async_f32(dst + 128u, __fmul_rn(dq1, dq1), bar);
-        }
-      }
+      //      plane, 16-byte chunks XORed with k & 7); quant_raw / quant_st as full 128-byte lines.  This part needs
+      //      nothing from the other CTAs, so it runs BEFORE the wait for the inbox.
       float* qr = quant_raw + (int64_t)row_w * row_pitch + h * VU_DIM + lane;
       float* qs = quant_st + (int64_t)row_w * row_pitch + h * VU_DIM + lane;
       const int n_ok = n_rows - row_w;                     // rows i < n_ok exist
@@ -399,48 +398,68 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
           qs += row_pitch;
         }
       }
+      // the owners have summed the previous tile (the other group's): the inboxes may be overwritten.  The owners
+      // signal tile t on inbox_free[t & 1], so each group watches ONE barrier and sees every one of its phases (with
+      // a single barrier a group could be 0, 1 or 2 phases behind, which a parity wait cannot tell apart).
+      if (it > 0) mbar_wait_cluster(inbox_free + ((it - 1) & 1u), ((it - 1) >> 1) & 1u);
+      // ---- push (q - z)^2 of the 32 rows to their owners (gathers the codewords again: 4 LDS per row)
+#pragma unroll
+      for (int i0 = 0; i0 < 32; i0 += 4) {
+        float q0[4], q1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = __shfl_sync(0xffffffffu, best_k, i0 + j);
+          const uint8_t* a = sBl + (uint32_t)k * 128u + (uint32_t)(((lx ^ k) & 7) << 4);
+          q0[j] = *reinterpret_cast<const float*>(a) + *reinterpret_cast<const float*>(a + B_PLANE);
+          q1[j] = *reinterpret_cast<const float*>(a + 2 * B_PLANE) + *reinterpret_cast<const float*>(a + 3 * B_PLANE);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j;
+          const float dq0 = q0[j] - z0[i], dq1 = q1[j] - z1[i];
+          const uint32_t dst = (i < 16 ? dst_a + (uint32_t)i * 256u : dst_b + (uint32_t)(i - 16) * 256u);
+          const uint32_t bar = (i < 16 ? full_a : full_b);
+          st_async_f32(dst, __fmul_rn(dq0, dq0), bar);       // no fma contraction with the head sum
+          st_async_f32(dst + 128u, __fmul_rn(dq1, dq1), bar);
+        }
+      }
     }
   } else if (warp < VU_EPI / 32 + 2) {
     // ============================= operand staging (A): runs ahead, gated by a_free =============================
     const int st = tid - VU_EPI;                         // 0..63
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int row0 = tile * VU_ROWS;
-      if (it > 0) mbar_wait(a_free, (it - 1) & 1u);        // the previous tile's MMAs have read the stage
-      // A: 128 rows x 16 sixteen-byte chunks; consecutive threads read consecutive chunks of a row (256 B per row)
-#pragma unroll 8
-      for (int i = 0; i < (VU_ROWS * 16) / 64; ++i) {
-        const int e = st + 64 * i;
-        const int r = e >> 4, c_all = e & 15;
-        const int half = c_all >> 3, chunk = c_all & 7;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + r < n_rows)
-          x = __ldg(reinterpret_cast<const float4*>(z + (int64_t)(row0 + r) * ld_z + h * VU_DIM + c_all * 4));
-        const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-        uint8_t* d = sA + (half * 2) * A_PLANE + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
-                     (uint32_t)((chunk ^ (r & 7)) << 4);
-        *reinterpret_cast<float4*>(d) = hi;
-        *reinterpret_cast<float4*>(d + A_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
-      }
-      publish_and_arrive_warp(a_full);
+    uint32_t it = 1;                                     // (tile 0 was staged during the prologue)
+    for (int tile = blockIdx.x + gridDim.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      mbar_wait(a_free, (it - 1) & 1u);                    // the previous tile's MMAs have read the stage
+      stage_tile(tile, st);
     }
   } else if (warp < MMA_WARP) {
     // ================================ head sum of the commitment term ================================
     // this CTA owns rows [h*R, (h+1)*R) of every tile: sum the heads in head order, scale, write diff
     const int st = tid - VU_EPI - 64;                    // 0..63
+    const uint32_t inbox_sa = smem_u32(inbox);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int row0 = tile * VU_ROWS;
       mbar_wait_cluster(inbox_full, it & 1u);
       if (st == 0) mbar_arrive_expect_tx(inbox_full, VU_ROWS * VU_DIM * 4);    // the next tile's bytes
+      // sum of one float4 (row lr, dims 4*d4 ..) over the heads in head order; the loads of all heads are issued
+      // before the first add (the head count is a runtime value: predicated, fully unrolled)
       auto sum_item = [&](int e) {
-        const int lr = e >> 4, d4 = e & 15;
-        float4 a = *reinterpret_cast<const float4*>(inbox + (size_t)lr * VU_DIM + d4 * 4);
-        for (int hh = 1; hh < n_heads; ++hh) {
-          const float4 v = *reinterpret_cast<const float4*>(inbox + ((size_t)(hh << lgR) + lr) * VU_DIM + d4 * 4);
-          a.x = __fadd_rn(a.x, v.x); a.y = __fadd_rn(a.y, v.y);
-          a.z = __fadd_rn(a.z, v.z); a.w = __fadd_rn(a.w, v.w);
-        }
+        const uint32_t a0 = inbox_sa + (uint32_t)(((e >> 4) * VU_DIM + (e & 15) * 4) * 4);
+        float4 v[8];
+#pragma unroll
+        for (int hh = 0; hh < 8; ++hh)
+          if (hh < n_heads)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v[hh].x), "=f"(v[hh].y), "=f"(v[hh].z), "=f"(v[hh].w)
+                         : "r"(a0 + (uint32_t)((hh << lgR) * VU_DIM * 4)));
+        float4 a = v[0];
+#pragma unroll
+        for (int hh = 1; hh < 8; ++hh)
+          if (hh < n_heads) {
+            a.x = __fadd_rn(a.x, v[hh].x); a.y = __fadd_rn(a.y, v[hh].y);
+            a.z = __fadd_rn(a.z, v[hh].z); a.w = __fadd_rn(a.w, v[hh].w);
+          }
         return make_float4(a.x * inv_heads, a.y * inv_heads, a.z * inv_heads, a.w * inv_heads);
       };
       auto store_item = [&](int e, const float4& v) {

@@ -16,7 +16,11 @@ from . import lib as L
 CONV_MATH = os.environ.get("MSMC_CONV_MATH", "3xtf32")
 UMMA_MIN_ROWS = 256
 USE_TAP_REUSE = os.environ.get("MSMC_TAP_REUSE", "1") != "0"
-VQ_UMMA = os.environ.get("MSMC_VQ_UMMA", "0") == "1"     # experimental: see csrc/vq_umma.cu
+# VQ search kernel choice: "auto" = the two-phase tensor-core kernel (csrc/vq_umma.cu, bit-identical results) from
+# VQ_UMMA_MIN_ROWS rows on -- below that a launch is one row tile per CTA and the CUDA-core cluster kernel's shorter
+# prologue wins (profiles/r02_bench_vq_*.txt) --; True / "1" forces it, False / "0" disables it
+VQ_UMMA = {"0": False, "1": True}.get(os.environ.get("MSMC_VQ_UMMA", "auto"), "auto")
+VQ_UMMA_MIN_ROWS = int(os.environ.get("MSMC_VQ_UMMA_MIN_ROWS", "2048"))
 
 ConvCfg = namedtuple("ConvCfg", "KH KW sh sw dh dw ph pw reflect transposed wstr Cd pre_slope post out_hw")
 # wstr = element strides of the weight tensor for (kh, kw, cs, cd), cs = channels of the op's INPUT
@@ -640,9 +644,10 @@ class _VQFn(torch.autograd.Function):
         diff = torch.empty((n_rows, dim), dtype=torch.float32, device=z.device)
         idx = torch.empty((n_rows, n_heads), dtype=torch.int64, device=z.device)
         entry = "msmc_vq_search"
-        if VQ_UMMA and dim == 64 and K in (64, 128, 256) and n_heads in (1, 2, 4, 8) and z2.stride(0) % 4 == 0 \
+        use_umma = VQ_UMMA is True or (VQ_UMMA == "auto" and n_rows >= VQ_UMMA_MIN_ROWS)
+        if use_umma and dim == 64 and K in (64, 128, 256) and n_heads in (1, 2, 4, 8) and z2.stride(0) % 4 == 0 \
                 and z2.data_ptr() % 16 == 0:
-            entry = "msmc_vq_search_umma"      # experimental two-phase tensor-core search (default off)
+            entry = "msmc_vq_search_umma"      # two-phase tensor-core search
         L.call(entry, L.ptr(z2), C.c_int64(z2.stride(0)), L.ptr(embed), L.ptr(q_raw), L.ptr(q_st),
                L.ptr(diff), L.ptr(idx), n_rows, n_heads, dim, K)
         ctx.save_for_backward(z2, q_raw)

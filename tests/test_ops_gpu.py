@@ -191,9 +191,13 @@ def test_conv_swapped_spatial_axes_matches_reference_layout():
 @pytest.mark.parametrize("heads,K,n", [(4, 64, 3840), (4, 256, 960), (1, 64, 128), (2, 32, 48), (4, 100, 257),
                                        (4, 128, 3841), (4, 256, 20011), (4, 64, 19999), (4, 256, 7),
                                        (2, 64, 100), (8, 128, 77), (4, 128, 19200)])
-def test_vq_search_bit_exact_vs_c_oracle(heads, K, n):
+@pytest.mark.parametrize("kernel", ["cuda_core", "tensor_core"])
+def test_vq_search_bit_exact_vs_c_oracle(heads, K, n, kernel, monkeypatch):
     from msmctts._b200 import functional as Fn
     from oracle import vq as OV
+    # both search kernels at every shape (the tensor-core one covers dim 64, K in {64, 128, 256}; other shapes fall
+    # through to the CUDA-core kernels in either mode); the default policy switches between them by row count
+    monkeypatch.setattr(Fn, "VQ_UMMA", kernel == "tensor_core")
     dev = _dev()
     dim = 256 // heads if heads in (1, 4) else 64
     rng = np.random.default_rng(heads * 1000 + K)
@@ -472,11 +476,13 @@ def test_fused_adam_per_parameter_steps_and_fused_clip():
     assert [float(ours2.state_dict()["state"][i]["step"]) for i in range(4)] == [9.0, 5.0, 9.0, 5.0]
 
 
-def test_vq_search_nan_row_does_not_fault():
+@pytest.mark.parametrize("kernel", ["cuda_core", "tensor_core"])
+def test_vq_search_nan_row_does_not_fault(kernel, monkeypatch):
     """a diverged batch (NaN / Inf row) must yield an in-range index (the reference's (-dist).max(1) returns 0 for
     an all-NaN row) instead of reading far outside the codebook; the other rows are unaffected"""
     from msmctts._b200 import functional as Fn
     from oracle import vq as OV
+    monkeypatch.setattr(Fn, "VQ_UMMA", kernel == "tensor_core")
     dev = _dev()
     for heads, K, n in ((4, 256, 960), (4, 64, 3840), (4, 100, 257), (4, 256, 20011)):
         dim = 64
