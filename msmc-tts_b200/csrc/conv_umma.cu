@@ -439,6 +439,17 @@ constexpr int RU_ROWS = 192;                  // 128 output rows + up to 64 rows
 constexpr int RU_PRODUCERS = 256;
 constexpr int RU_THREADS = RU_PRODUCERS + 64;  // + MMA warp + weight-loader warp
 
+// ---- thread-block-cluster helpers (split-K over the source channels: the CTAs of a cluster share one output tile)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta_rank(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+
 struct ReuseArgs {
   msmc_conv_geom g;
   const float* src;
@@ -453,6 +464,7 @@ struct ReuseArgs {
   int tap_stride;        // rows between consecutive taps (dh * Ws or dw)
   int n_taps;
   int tiles_per_batch;
+  int k_splits;          // cluster (1, 1, k_splits): CTA z of a cluster takes the z-th slice of the channel chunks
 };
 
 
@@ -480,6 +492,11 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
   const int l0 = (blockIdx.x - b * a.tiles_per_batch) * UM_BM;
   const int n_tile = blockIdx.y, n_tiles = gridDim.y;
   const int KC = (g.Cs + UM_BK - 1) / UM_BK;
+  // split-K: launches with few output tiles and a long channel loop (FFN second conv: 60 tiles x 96 MMA steps) run
+  // as clusters of KS CTAs per tile; CTA ks reduces chunks [kc_beg, kc_end), CTA 0 sums the accumulators (in rank
+  // order, through its own shared memory) and runs the epilogue
+  const int KS = a.k_splits, ks = blockIdx.z;
+  const int kc_beg = (KC * ks) / KS, kc_end = (KC * (ks + 1)) / KS;
   const int T = a.n_taps;
   const int r_in = UM_BM + (T - 1) * a.tap_stride;      // rows staged per chunk (<= RU_ROWS)
   constexpr int MMA_WARP = RU_PRODUCERS / 32;   // warp MMA_WARP + 1 streams the weight tiles
@@ -526,11 +543,11 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
         }
       }
     };
-    gather(0);
+    gather(kc_beg);
     int sa = 0;
     uint32_t pa = 0;
     const uint32_t dst_off = (uint32_t)(rsub >> 3) * 1024u + (uint32_t)r8 * 128u + (uint32_t)((chunk ^ r8) << 4);
-    for (int kc = 0; kc < KC; ++kc) {
+    for (int kc = kc_beg; kc < kc_end; ++kc) {
       mbar_wait(&ea[sa], pa ^ 1u);
       uint8_t* dstbase = sA + sa * A_BYTES + dst_off;
 #pragma unroll
@@ -547,27 +564,111 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
           }
         }
       }
-      if (kc + 1 < KC) gather(kc + 1);
+      if (kc + 1 < kc_end) gather(kc + 1);
       publish_and_arrive_warp(&fa[sa]);
       if (++sa == NA) { sa = 0; pa ^= 1u; }
     }
+    mbar_wait(accum_bar, 0);          // this CTA's MMAs are complete (its operand stages are dead)
+    tc_fence_after();
+  } else if (warp == MMA_WARP) {
+    // ================================= MMA issuer =================================
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(UM_BM >> 4) << 24);
+    {
+      const uint32_t elected = elect_one();     // convergent, predicated issue (see umma_tf32_pred)
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const uint32_t a_desc0 = desc_lo_k(smem_u32(sA)), b_desc0 = desc_lo_k(smem_u32(sB));
+      for (int kc = kc_beg; kc < kc_end; ++kc) {
+        mbar_wait(&fa[sa], pa);
+        // tap = row shift of the staged tile: the descriptor start moves by tap_stride rows of 128 B (8 units); the
+        // swizzle is a function of the absolute shared-memory address, so the base-offset field stays 0
+        uint32_t ad = a_desc0 + (uint32_t)sa * (A_BYTES >> 4);
+        const uint32_t a_step = (uint32_t)a.tap_stride * 8u;
+        for (int t = 0; t < T; ++t, ad += a_step) {
+          mbar_wait(&fb[sb], pb);
+          tc_fence_after();
+          const uint32_t bd = b_desc0 + (uint32_t)sb * (B_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < UM_BK / 8; ++k) {
+            const uint32_t a_hi = ad + 2 * k, b_hi = bd + 2 * k;
+            const uint32_t acc = (kc > kc_beg || t > 0 || k > 0) ? 1u : 0u;
+            if (SPLIT) {
+              const uint32_t a_lo = a_hi + (A_PLANE >> 4), b_lo = b_hi + (B_PLANE >> 4);
+              umma_tf32_pred<DESC_HI_K>(tmem_base, a_lo, b_hi, IDESC, acc, elected);
+              umma_tf32_pred<DESC_HI_K>(tmem_base, a_hi, b_lo, IDESC, 1u, elected);
+              umma_tf32_pred<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, 1u, elected);
+            } else {
+              umma_tf32_pred<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, acc, elected);
+            }
+          }
+          umma_commit_pred(&eb[sb], elected);
+          if (++sb == NBS) { sb = 0; pb ^= 1u; }
+        }
+        umma_commit_pred(&ea[sa], elected);
+        if (++sa == NA) { sa = 0; pa ^= 1u; }
+      }
+      umma_commit_pred(accum_bar, elected);
+    }
+    __syncwarp();
+  } else {
+    // ================================= weight-tile loader =================================
+    if ((tid & 31) == 0) {
+      int sb = 0;
+      uint32_t pb = 0;
+      for (int kc = kc_beg; kc < kc_end; ++kc)
+        for (int t = 0; t < T; ++t) {
+          mbar_wait(&eb[sb], pb ^ 1u);
+          mbar_arrive_expect_tx(&fb[sb], B_BYTES);
+          const float* wsrc = a.wimg + (((int64_t)t * KC + kc) * n_tiles + n_tile) * (B_BYTES / 4);
+          bulk_g2s(sB + sb * B_BYTES, wsrc, B_BYTES, &fb[sb]);
+          if (++sb == NBS) { sb = 0; pb ^= 1u; }
+        }
+    }
+    __syncwarp();
+  }
 
+  // ============ split-K: the accumulators of CTAs 1 .. KS-1 travel to CTA 0's (now dead) operand stages ============
+  // layout per partial: [column][128 rows] fp32 -- a warp's 32 rows are one 128-byte line on both sides
+  const int lane_grp = warp & 3;
+  const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+  constexpr int CHALF = BN / 2;
+  const int cbeg = (warp >> 2) * CHALF;
+  const int erow = lane_grp * 32 + (tid & 31);      // accumulator row of this thread (epilogue warps)
+  if (KS > 1) {
+    cluster_sync_all();               // every CTA of the cluster has finished its MMAs
+    if (ks > 0 && warp < MMA_WARP) {
+      const uint32_t dst0 = map_to_cta_rank(smem_u32(smem) + (uint32_t)(ks - 1) * (uint32_t)(BN * UM_BM * 4), 0u) +
+                            (uint32_t)erow * 4u;
+#pragma unroll 1
+      for (int c0 = cbeg; c0 < cbeg + CHALF; c0 += 16) {
+        float acc[16];
+        tmem_ld16(taddr + (uint32_t)c0, acc);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(dst0 + (uint32_t)((c0 + j) * UM_BM * 4)), "f"(acc[j])
+                       : "memory");
+      }
+      tc_fence_before();
+    }
+    cluster_sync_all();               // the partials have landed (release / acquire at cluster scope)
+  }
+
+  if (warp < MMA_WARP && ks == 0) {
     // ================================= epilogue =================================
-    const int lane_grp = warp & 3;
-    const int l = l0 + lane_grp * 32 + (tid & 31);
+    const int l = l0 + erow;
     const bool row_ok = l < a.Ld;
     const int64_t m = (int64_t)b * a.Ld + l;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
     const int n0 = n_tile * BN;
     const bool dneed_aux = xf_needs_aux(g.dst_xf);
-    constexpr int CHALF = BN / 2;
-    const int cbeg = (warp >> 2) * CHALF;
+    const float* part = reinterpret_cast<const float*>(smem) + erow;
 #pragma unroll 1
     for (int c0 = cbeg; c0 < cbeg + CHALF; c0 += 16) {
       float acc[16];
       tmem_ld16(taddr + (uint32_t)c0, acc);
+      for (int p = 0; p < KS - 1; ++p)              // rank order: (acc0 + acc1) + acc2 ...
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += part[(p * BN + c0 + j) * UM_BM];
       if (row_ok) {
         const bool full16 = n0 + c0 + 16 <= g.Cd;
         if (full16 && (!dneed_aux || ((g.ld_daux & 3) == 0 && (reinterpret_cast<uintptr_t>(a.dst_aux) & 15) == 0)) && (g.ld_dst & 3) == 0 && (!a.residual || (g.ld_res & 3) == 0)) {
@@ -621,62 +722,6 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
       }
     }
     tc_fence_before();
-  } else if (warp == MMA_WARP) {
-    // ================================= MMA issuer =================================
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                               ((uint32_t)(UM_BM >> 4) << 24);
-    {
-      const uint32_t elected = elect_one();     // convergent, predicated issue (see umma_tf32_pred)
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      const uint32_t a_desc0 = desc_lo_k(smem_u32(sA)), b_desc0 = desc_lo_k(smem_u32(sB));
-      for (int kc = 0; kc < KC; ++kc) {
-        mbar_wait(&fa[sa], pa);
-        // tap = row shift of the staged tile: the descriptor start moves by tap_stride rows of 128 B (8 units); the
-        // swizzle is a function of the absolute shared-memory address, so the base-offset field stays 0
-        uint32_t ad = a_desc0 + (uint32_t)sa * (A_BYTES >> 4);
-        const uint32_t a_step = (uint32_t)a.tap_stride * 8u;
-        for (int t = 0; t < T; ++t, ad += a_step) {
-          mbar_wait(&fb[sb], pb);
-          tc_fence_after();
-          const uint32_t bd = b_desc0 + (uint32_t)sb * (B_BYTES >> 4);
-#pragma unroll
-          for (int k = 0; k < UM_BK / 8; ++k) {
-            const uint32_t a_hi = ad + 2 * k, b_hi = bd + 2 * k;
-            const uint32_t acc = (kc > 0 || t > 0 || k > 0) ? 1u : 0u;
-            if (SPLIT) {
-              const uint32_t a_lo = a_hi + (A_PLANE >> 4), b_lo = b_hi + (B_PLANE >> 4);
-              umma_tf32_pred<DESC_HI_K>(tmem_base, a_lo, b_hi, IDESC, acc, elected);
-              umma_tf32_pred<DESC_HI_K>(tmem_base, a_hi, b_lo, IDESC, 1u, elected);
-              umma_tf32_pred<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, 1u, elected);
-            } else {
-              umma_tf32_pred<DESC_HI_K>(tmem_base, a_hi, b_hi, IDESC, acc, elected);
-            }
-          }
-          umma_commit_pred(&eb[sb], elected);
-          if (++sb == NBS) { sb = 0; pb ^= 1u; }
-        }
-        umma_commit_pred(&ea[sa], elected);
-        if (++sa == NA) { sa = 0; pa ^= 1u; }
-      }
-      umma_commit_pred(accum_bar, elected);
-    }
-    __syncwarp();
-  } else {
-    // ================================= weight-tile loader =================================
-    if ((tid & 31) == 0) {
-      int sb = 0;
-      uint32_t pb = 0;
-      for (int kc = 0; kc < KC; ++kc)
-        for (int t = 0; t < T; ++t) {
-          mbar_wait(&eb[sb], pb ^ 1u);
-          mbar_arrive_expect_tx(&fb[sb], B_BYTES);
-          const float* wsrc = a.wimg + (((int64_t)t * KC + kc) * n_tiles + n_tile) * (B_BYTES / 4);
-          bulk_g2s(sB + sb * B_BYTES, wsrc, B_BYTES, &fb[sb]);
-          if (++sb == NBS) { sb = 0; pb ^= 1u; }
-        }
-    }
-    __syncwarp();
   }
   __syncthreads();
   if (warp == MMA_WARP) {
@@ -1719,7 +1764,19 @@ extern "C" int msmc_conv_forward_umma_reuse(const msmc_conv_geom* gp, const floa
   a.dst_aux = dst_aux; a.dst = dst;
   a.Ls = g.Hs * g.Ws; a.Ld = g.Hd * g.Wd;
   a.tiles_per_batch = ceil_div(a.Ld, UM_BM);
-  dim3 grid((unsigned)(a.tiles_per_batch * g.B), (unsigned)ceil_div(g.Cd, BN));
+  // split-K clusters where a launch has few output tiles and a long channel loop (each CTA then runs KC/KS chunks):
+  // as many splits (2 or 4) as keep the grid within one wave and leave >= 4 chunks per CTA.  MSMC_REUSE_KSPLIT=1/2/4
+  // forces it (read per call: the A/B tools switch it).
+  const int KCh = ceil_div(g.Cs, UM_BK);
+  const int64_t out_tiles = (int64_t)a.tiles_per_batch * g.B * ceil_div(g.Cd, BN);
+  int KS = 1;
+  while (KS < 4 && out_tiles * (KS * 2) <= num_sms() && KCh / (KS * 2) >= 4) KS *= 2;
+  if (const char* e_ks = getenv("MSMC_REUSE_KSPLIT")) {
+    const int v = atoi(e_ks);
+    if (v == 1 || ((v == 2 || v == 4) && KCh >= v)) KS = v;
+  }
+  a.k_splits = KS;
+  dim3 grid((unsigned)(a.tiles_per_batch * g.B), (unsigned)ceil_div(g.Cd, BN), (unsigned)KS);
   cudaStream_t st = (cudaStream_t)stream;
   const int xfc = g.src_xf == MSMC_XF_NONE ? XFC_NONE
                   : (g.src_xf == MSMC_XF_LRELU && g.src_slope > 0.f && g.src_slope < 1.f) ? XFC_LRELU : XFC_GENERIC;
@@ -1727,9 +1784,20 @@ extern "C" int msmc_conv_forward_umma_reuse(const msmc_conv_geom* gp, const floa
   do {                                                                                                            \
     const size_t smem = 1024 + (size_t)(SPLIT_ ? 2 : 1) * ((size_t)NA_ * RU_ROWS * 128 + (size_t)NB_ * BN_ * 128) + \
                         (2 * NA_ + 2 * NB_ + 1) * 8 + 16;                                                         \
+    /* the partial accumulators of the split-K peers land in the operand stages */                               \
+    if ((size_t)(KS - 1) * BN_ * UM_BM * 4 >                                                                      \
+        (size_t)(SPLIT_ ? 2 : 1) * ((size_t)NA_ * RU_ROWS * 128 + (size_t)NB_ * BN_ * 128))                       \
+      return MSMC_ERR_UNSUPPORTED;                                                                                \
     cudaFuncSetAttribute(conv_umma_reuse_kernel<BN_, SPLIT_, NA_, NB_, X_>,                                       \
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                 \
-    conv_umma_reuse_kernel<BN_, SPLIT_, NA_, NB_, X_><<<grid, RU_THREADS, smem, st>>>(a);                         \
+    cudaLaunchConfig_t cfg = {};                                                                                  \
+    cfg.gridDim = grid; cfg.blockDim = dim3(RU_THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;      \
+    cudaLaunchAttribute attr[1];                                                                                  \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                             \
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)KS;          \
+    cfg.attrs = attr; cfg.numAttrs = KS > 1 ? 1 : 0;                                                              \
+    if (cudaLaunchKernelEx(&cfg, conv_umma_reuse_kernel<BN_, SPLIT_, NA_, NB_, X_>, a) != cudaSuccess)            \
+      return MSMC_ERR_LAUNCH;                                                                                     \
   } while (0)
 #define LAUNCH_RU(BN_, SPLIT_, NA_, NB_)                                       \
   do {                                                                         \

@@ -22,7 +22,9 @@ CASES = {
     "ffn2": (16, 240, 1024, 256, 3, 1, False),
     "ffn2_60": (16, 60, 1024, 256, 3, 1, False),
 }
-CONFIGS = [("one-tile", {"MSMC_REUSE_PERSIST": "0"}),
+CONFIGS = [("one-tile", {"MSMC_REUSE_PERSIST": "0", "MSMC_REUSE_KSPLIT": "1"}),
+           ("one-tile-ks2", {"MSMC_REUSE_PERSIST": "0", "MSMC_REUSE_KSPLIT": "2"}),
+           ("one-tile-ks4", {"MSMC_REUSE_PERSIST": "0", "MSMC_REUSE_KSPLIT": "4"}),
            ("persist-auto", {"MSMC_REUSE_PERSIST": "1"}),
            ("persist-nacc1", {"MSMC_REUSE_PERSIST": "1", "MSMC_PERSIST_NACC": "1"}),
            ("persist-nacc2", {"MSMC_REUSE_PERSIST": "1", "MSMC_PERSIST_NACC": "2"}),
@@ -43,7 +45,7 @@ for name in names:
     byt = 4.0 * (B * L * (Ci + Co * (2 if use_res else 1)) + K * Ci * Co)
     row = []
     for cname, env in CONFIGS:
-        for k in ("MSMC_REUSE_PERSIST", "MSMC_PERSIST_NACC", "MSMC_PERSIST_NBS"):
+        for k in ("MSMC_REUSE_PERSIST", "MSMC_PERSIST_NACC", "MSMC_PERSIST_NBS", "MSMC_REUSE_KSPLIT"):
             os.environ.pop(k, None)
         os.environ.update(env)
         if extra:

@@ -196,6 +196,7 @@ def test_persistent_reuse_kernel_vs_one_tile_kernel_and_cpu(shape, nacc, monkeyp
     wgt = torch.randn(B, 1, Ln, Co, generator=gen)
     pad = (K * d - d) // 2
     outs = []
+    monkeypatch.setenv("MSMC_REUSE_KSPLIT", "1")     # (split-K clusters change the summation order)
     for persist in ("1", "0"):
         monkeypatch.setenv("MSMC_REUSE_PERSIST", persist)
         if nacc:
@@ -216,3 +217,49 @@ def test_persistent_reuse_kernel_vs_one_tile_kernel_and_cpu(shape, nacc, monkeyp
     (y_ref * wgt).sum().backward()
     close(outs[0][0], y_ref, 2e-5, "y vs cpu")
     close(outs[0][1], xr.grad, 2e-5, "dx vs cpu")
+
+
+@pytest.mark.parametrize("ks", [0, 2, 4], ids=["auto", "ks2", "ks4"])
+@pytest.mark.parametrize("shape", [(16, 240, 1024, 256, 3, 1, False),    # FFN second conv: 64 tiles x 96 MMA steps
+                                   (16, 60, 1024, 256, 3, 1, False),     # short sequences: 32 tiles
+                                   (16, 240, 256, 256, 11, 5, True),     # MRF, 8 chunks x 11 taps
+                                   (3, 200, 160, 72, 5, 1, False)],      # ragged channels, 5 chunks
+                         ids=["ffn2", "ffn2_T60", "mrf256k11", "ragged"])
+def test_split_k_cluster_reuse_kernel(shape, ks, monkeypatch):
+    """split-K thread-block clusters of the tap-reuse kernel (CTA z reduces its slice of the 32-channel chunks, the
+    accumulators of CTAs 1.. travel through distributed shared memory to CTA 0, which sums them in rank order and
+    runs the epilogue): forward and stride-1 data gradient vs torch fp32 on the CPU (2e-5 of the tensor max) and vs
+    the unsplit kernel (4e-5: two results that are each within 2e-5 of the reference; the summation order differs)."""
+    from msmctts._b200 import functional as Fn
+    monkeypatch.setattr(Fn, "CONV_MATH", "3xtf32")
+    monkeypatch.setenv("MSMC_REUSE_PERSIST", "0")
+    B, Ln, Ci, Co, K, d, use_res = shape
+    gen = torch.Generator().manual_seed(Ln + Ci + K)
+    x = torch.randn(B, 1, Ln, Ci, generator=gen)
+    w = torch.randn(1, K, Ci, Co, generator=gen) / (Ci * K) ** 0.5
+    bias = torch.randn(Co, generator=gen) * 0.1
+    res = torch.randn(B, 1, Ln, Co, generator=gen) if use_res else None
+    wgt = torch.randn(B, 1, Ln, Co, generator=gen)
+    pad = (K * d - d) // 2
+    outs = []
+    for split in ([str(ks)] if ks else [None]) + ["1"]:
+        if split is None:
+            monkeypatch.delenv("MSMC_REUSE_KSPLIT", raising=False)
+        else:
+            monkeypatch.setenv("MSMC_REUSE_KSPLIT", split)
+        xc = x.to(DEV).requires_grad_(True)
+        y = Fn.conv_cl(xc, w.to(DEV), bias.to(DEV), res.to(DEV) if use_res else None, kernel=(1, K),
+                       dilation=(1, d), padding=(0, pad), pre_slope=0.1)
+        (y * wgt.to(DEV)).sum().backward()
+        torch.cuda.synchronize()
+        outs.append((y.detach(), xc.grad.detach()))
+    xr = x.clone().requires_grad_(True)
+    y_ref = F.conv1d(F.leaky_relu(xr[:, 0].transpose(1, 2), 0.1), w[0].permute(2, 1, 0).contiguous(), bias,
+                     padding=pad, dilation=d).transpose(1, 2).unsqueeze(1)
+    if use_res:
+        y_ref = y_ref + res
+    (y_ref * wgt).sum().backward()
+    close(outs[0][0], y_ref, 2e-5, "y vs cpu")
+    close(outs[0][1], xr.grad, 2e-5, "dx vs cpu")
+    close(outs[0][0], outs[1][0], 4e-5, "y vs unsplit")      # (each is within 2e-5 of the fp32 reference)
+    close(outs[0][1], outs[1][1], 4e-5, "dx vs unsplit")
