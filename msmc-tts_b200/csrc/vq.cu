@@ -521,12 +521,27 @@ vq_ema_accum_kernel(const float* __restrict__ z, int64_t ld_z, const int64_t* __
     }
     unsigned m = __ballot_sync(0xffffffffu, hit);
     while (m) {
-      const int s = __ffs(m) - 1;
-      m &= m - 1;
-      const float* zr = z + (int64_t)(r0 + s) * ld_z + h * DIM;
+      // up to four hit rows per round trip (synthetic / early-training batches put hundreds of rows on one
+      // codeword: one dependent load per hit made this kernel latency-bound); accumulated in row order
+      int sr[4];
+      float v[4][DPL];
 #pragma unroll
-      for (int j = 0; j < DPL; ++j) acc[j] += zr[lane + 32 * j];
-      cnt += 1.f;
+      for (int u = 0; u < 4; ++u) {
+        sr[u] = m ? __ffs(m) - 1 : -1;
+        m &= m - 1;            // (0 stays 0)
+        if (sr[u] >= 0) {
+          const float* zr = z + (int64_t)(r0 + sr[u]) * ld_z + h * DIM;
+#pragma unroll
+          for (int j = 0; j < DPL; ++j) v[u][j] = zr[lane + 32 * j];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (sr[u] >= 0) {
+#pragma unroll
+          for (int j = 0; j < DPL; ++j) acc[j] += v[u][j];
+          cnt += 1.f;
+        }
     }
   }
 #pragma unroll
@@ -552,7 +567,7 @@ template <int DIM>
 __global__ void __launch_bounds__(256)
 vq_ema_finalize_kernel(const float* __restrict__ cluster_size, const float* __restrict__ embed_avg,
                        float* __restrict__ embed, int K, float eps) {
-  const int h = blockIdx.x;
+  const int h = blockIdx.x;       // gridDim.y CTAs share a head (each recomputes n: K loads)
   __shared__ float s_n;
   if (threadIdx.x < 32) {
     // fixed-order sum: lane-strided partials, then a shuffle tree
@@ -563,7 +578,7 @@ vq_ema_finalize_kernel(const float* __restrict__ cluster_size, const float* __re
   }
   __syncthreads();
   const float n = s_n;
-  for (int e = threadIdx.x; e < DIM * K; e += blockDim.x) {
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < DIM * K; e += gridDim.y * blockDim.x) {
     const int k = e % K;
     const float cs = (cluster_size[(size_t)h * K + k] + eps) / (n + K * eps) * n;
     embed[(size_t)h * DIM * K + e] = embed_avg[(size_t)h * DIM * K + e] / cs;
@@ -791,7 +806,7 @@ extern "C" int msmc_vq_ema_update(const float* z, int64_t ld_z, const int64_t* i
   do {                                                                                                       \
     vq_ema_accum_kernel<D><<<n_heads * n_embed, 256, 0, st>>>(z, ld_z, idx, lengths, batch, t, n_heads,      \
                                                                n_embed, decay, cluster_size, embed_avg);      \
-    vq_ema_finalize_kernel<D><<<n_heads, 256, 0, st>>>(cluster_size, embed_avg, embed, n_embed, eps);        \
+    vq_ema_finalize_kernel<D><<<dim3(n_heads, 16), 256, 0, st>>>(cluster_size, embed_avg, embed, n_embed, eps);        \
   } while (0)
   switch (dim) {
     case 32: LAUNCH_EMA(32); break;
