@@ -781,54 +781,46 @@ int small_wgrad_splits(const msmc_conv_geom& g) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(M, 2 * SW_TP), (int64_t)num_sms() * 4));
 }
 
-// VEC = 4 when Cd is a multiple of 4: one 16-byte load per slice and one index decomposition per four outputs
-// (the scalar form paid two 64-bit divisions per element and ran at ~0.9 TB/s: 204 launches, 2.5 ms per step)
-template <int VEC>
-__global__ void wgrad_reduce_kernel(const msmc_conv_geom g, const float* __restrict__ partial, int splits,
-                                    float* __restrict__ dw, float* __restrict__ dbias) {
+// 64 outputs per CTA x 4 slice groups: group y sums slices y, y + 4, ... (four loads in flight), the groups are
+// combined in fixed order through shared memory -- deterministic, and a quarter of the serial walk over the slices
+// that bounds these small launches (12.5 us average, 204 per step, on the weight-gradient join of every conv backward)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const msmc_conv_geom g, const float* __restrict__ partial, int splits,
+                    float* __restrict__ dw, float* __restrict__ dbias) {
   const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
   const int64_t per = Ktot * g.Cd + g.Cd;
-  const int64_t total = (dbias ? per : Ktot * g.Cd) / VEC;
-  for (int64_t ev = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ev < total;
-       ev += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e = ev * VEC;
-    // fixed summation order (deterministic); eight independent loads in flight instead of one
-    float s[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) s[v] = 0.f;
-    int z = 0;
-    for (; z + 8 <= splits; z += 8) {
-      float t[8][VEC];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (VEC == 4) {
-          const float4 x = *reinterpret_cast<const float4*>(partial + (int64_t)(z + i) * per + e);
-          t[i][0] = x.x; t[i][1 % VEC] = x.y; t[i][2 % VEC] = x.z; t[i][3 % VEC] = x.w;
-        } else {
-          t[i][0] = partial[(int64_t)(z + i) * per + e];
-        }
+  const int64_t total = dbias ? per : Ktot * g.Cd;
+  __shared__ float red[4][64];
+  const int ex = threadIdx.x & 63, gy = threadIdx.x >> 6;
+  for (int64_t e0 = (int64_t)blockIdx.x * 64; e0 < total; e0 += (int64_t)gridDim.x * 64) {
+    const int64_t e = e0 + ex;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (e < total) {
+      int z = gy;
+      for (; z + 12 < splits; z += 16) {
+        s0 += partial[(int64_t)z * per + e];
+        s1 += partial[(int64_t)(z + 4) * per + e];
+        s2 += partial[(int64_t)(z + 8) * per + e];
+        s3 += partial[(int64_t)(z + 12) * per + e];
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) s[v] += t[i][v];
+      for (; z < splits; z += 4) s0 += partial[(int64_t)z * per + e];
     }
-    for (; z < splits; ++z)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) s[v] += partial[(int64_t)z * per + e + v];
-    if (e < Ktot * g.Cd) {
-      const uint32_t k = (uint32_t)(e / g.Cd);             // (Ktot < 2^31)
-      const int n = (int)(e - (int64_t)k * g.Cd);
-      const int t = (int)(k / (uint32_t)g.Cs);
-      const int c = (int)(k - (uint32_t)t * (uint32_t)g.Cs);
-      const int kh = t / g.KW, kw = t - kh * g.KW;
-      float* o = dw + kh * g.ws_kh + kw * g.ws_kw + c * g.ws_cs + (int64_t)n * g.ws_cd;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) o[(int64_t)v * g.ws_cd] = s[v];
-    } else {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) dbias[e - Ktot * g.Cd + v] = s[v];
+    red[gy][ex] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (gy == 0 && e < total) {
+      const float s = ((red[0][ex] + red[1][ex]) + red[2][ex]) + red[3][ex];
+      if (e < Ktot * g.Cd) {
+        const int64_t k = e / g.Cd;
+        const int n = (int)(e - k * g.Cd);
+        const int t = (int)(k / g.Cs);
+        const int c = (int)(k - (int64_t)t * g.Cs);
+        const int kh = t / g.KW, kw = t - kh * g.KW;
+        dw[kh * g.ws_kh + kw * g.ws_kw + c * g.ws_cs + (int64_t)n * g.ws_cd] = s;
+      } else {
+        dbias[e - Ktot * g.Cd] = s;
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -960,10 +952,10 @@ int launch_wgrad_reduce(const msmc_conv_geom& g, const float* workspace, int spl
                         void* stream) {
   const int64_t Ktot = (int64_t)g.KH * g.KW * g.Cs;
   const int64_t total = Ktot * g.Cd + g.Cd;
-  const bool vec4 = g.Cd % 4 == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0;
-  int blocks = (int)std::min<int64_t>(ceil_div64(vec4 ? total / 4 : total, 256), (int64_t)num_sms() * 8);
-  if (vec4) wgrad_reduce_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, workspace, splits, dw, dbias);
-  else wgrad_reduce_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, workspace, splits, dw, dbias);
+  // (a 4-wide variant -- one 16-byte load per slice, a quarter of the threads -- measured 2x slower per launch:
+  //  these launches are latency-bound on the serial walk over the slices and live on thread count)
+  int blocks = (int)std::min<int64_t>(ceil_div64(total, 64), (int64_t)num_sms() * 8);
+  wgrad_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, workspace, splits, dw, dbias);
   MSMC_CHECK_LAUNCH();
   return MSMC_OK;
 }
