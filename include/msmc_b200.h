@@ -141,10 +141,11 @@ int msmc_reflect_pad_fold(const float* gpad, float* gx, int32_t B, int32_t H, in
 int msmc_vq_search(const float* z, int64_t ld_z, const float* embed, float* quant_raw, float* quant_st,
                    float* diff, int64_t* idx, int32_t n_rows, int32_t n_heads, int32_t dim,
                    int32_t n_embed, void* stream);
-/* EXPERIMENTAL (default off, MSMC_VQ_UMMA=1): the same search, results identical by construction, as a two-phase
- * kernel -- all codewords scored on the tensor cores (tcgen05, 3xTF32), candidates within a provable margin of the
- * row minimum re-scored with the exact sequential-fma arithmetic.  dim = 64, n_embed in {64, 128, 256}, <= 8 heads,
- * ld_z a multiple of 4, 16-byte aligned pointers; MSMC_ERR_UNSUPPORTED otherwise. */
+/* The same search, results identical by construction, as a two-phase tensor-core kernel (the host side selects it
+ * from 2048 rows on; csrc/vq_umma.cu) -- all codewords scored with tcgen05 (3xTF32), the minimum accepted when the
+ * runner-up lies outside a provable margin, any other row re-scored with the exact sequential-fma arithmetic.
+ * dim = 64, n_embed in {64, 128, 256}, 1 / 2 / 4 / 8 heads, ld_z a multiple of 4, 16-byte aligned pointers;
+ * MSMC_ERR_UNSUPPORTED otherwise. */
 int msmc_vq_search_umma(const float* z, int64_t ld_z, const float* embed, float* quant_raw, float* quant_st,
                         float* diff, int64_t* idx, int32_t n_rows, int32_t n_heads, int32_t dim, int32_t n_embed,
                         void* stream);
