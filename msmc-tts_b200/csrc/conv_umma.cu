@@ -759,8 +759,16 @@ struct UmmaWgradArgs {
 };
 
 // (A K-major variant -- producers transposing both operands with warp shuffles -- was measured slower and removed.)
+// Producer warps: 8 (two CTAs per SM at BN <= 64) or 16 at BN = 128 (one CTA per SM: with 8 producer warps the SM
+// held 9 warps whose every issue waited ~8 cycles -- long scoreboard 3.0, wait 2.0, instruction fetch 1.1 -- and the
+// tensor pipe sat at 15 %; two warps per operand block, 16 positions each, halve the registers per thread and double
+// the loads in flight).
 template <int BN, bool SPLIT, int STAGES, int XFC>
-__global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_umma_kernel(const UmmaWgradArgs a) {
+__global__ void __launch_bounds__((BN == 128 ? 16 : 8) * 32 + 32, (BN <= 64 ? 2 : 1))
+conv_wgrad_umma_kernel(const UmmaWgradArgs a) {
+  constexpr int PW = (BN == 128 ? 16 : 8);     // producer / epilogue warps
+  constexpr int PH = PW / 8;                   // warps per operand block (each takes 32 / PH positions of a stage)
+  constexpr int NR = 8 / PH;                   // 16-byte loads per thread, operand and stage
   const msmc_conv_geom& g = a.g;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -787,11 +795,12 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
   const int64_t mbeg = (int64_t)blockIdx.z * a.rows_per_split;
   const int64_t mend = min(M, mbeg + a.rows_per_split);
   const int n_k = (int)((mend - mbeg + 31) / 32);      // stages of 32 positions (>= 1 by construction)
-  constexpr int MMA_WARP = UMF_PRODUCERS / 32;
+  constexpr int MMA_WARP = PW;
+  __shared__ float s_bias[4][2][32];          // per-half bias partials when two warps share an operand block
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], UMF_PRODUCERS / 32);
+      mbar_init(&full_bar[s], PW);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(accum_bar, 1);
@@ -809,11 +818,13 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform -> uniform register
 
   if (warp < MMA_WARP) {
-    // =============== producers: warps 0-3 stage the source operand, warps 4-7 the output-gradient operand ===============
-    // warp (mod 4) = 32-channel block; inside the warp one instruction reads 4 positions x 128 B:
-    // thread owns 16-byte chunk (lane & 7) of positions (lane >> 3) + 4*i, i = 0..7.
-    const bool is_a = warp < 4;
-    const int blk = warp & 3;
+    // ======= producers: the first PW/2 warps stage the source operand, the others the output-gradient operand =======
+    // PH warps per 32-channel block; inside the warp one instruction reads 4 positions x 128 B:
+    // thread owns 16-byte chunk (lane & 7) of positions half*(32/PH) + (lane >> 3) + 4*i, i = 0..NR-1.
+    const bool is_a = warp < PW / 2;
+    const int wsub = warp % (PW / 2);
+    const int blk = wsub / PH;                 // 32-channel block of this warp's operand
+    const int half = wsub % PH;                // which 32 / PH positions of every stage
     const int chunk = lane & 7;
     const int psub = lane >> 3;                // 0..3
     // A side: which (tap, channel block) this warp stages
@@ -832,9 +843,9 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
     const bool active = is_a ? true : nb_ok;
     // one stage of loads in flight per thread (two stages cost 128 registers here and spilled to local memory:
     // the ncu capture in profiles/ showed 400 MB of DRAM writes from the spill traffic alone)
-    float4 v[8], u[8];
+    float4 v[NR], u[NR];
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-    int64_t m_next = mbeg + psub;              // position of row i = 0 of the next stage to gather
+    int64_t m_next = mbeg + half * (4 * NR) + psub;     // position of row i = 0 of the next stage to gather
     const bool small_w = g.Wd < 4;             // carry-propagating decode below needs Wd >= 4
 
     auto gather = [&]() {
@@ -848,7 +859,7 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
         b = (int)bb; hd = (int)hh; wd = (int)(rem - hh * a.div_w.d);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < NR; ++i) {
         const int64_t m = m_next + 4 * i;
         const bool m_ok = m < mend;
         if (is_a) {
@@ -908,8 +919,8 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
         uint8_t* base = (is_a ? sA + s * A_BYTES : sB + s * B_BYTES) + (uint32_t)blk * 4096u;
         constexpr int PLANE_A = A_PLANE, PLANE_B = B_PLANE;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int p = psub + 4 * i;            // position within the stage = K index
+        for (int i = 0; i < NR; ++i) {
+          const int p = half * (4 * NR) + psub + 4 * i;      // position within the stage = K index
           float4 x;
           if (is_a) {
             x = xf4<XFC>(g, v[i], NEED_AUX ? u[i] : make_float4(0.f, 0.f, 0.f, 0.f));
@@ -942,29 +953,47 @@ __global__ void __launch_bounds__(UMF_THREADS, (BN <= 64 ? 2 : 1)) conv_wgrad_um
 
     // ================================= epilogue =================================
     float* part = a.partial + (int64_t)blockIdx.z * (Ktot * g.Cd + g.Cd);
-    if (do_bias) {
-      // lanes sharing a chunk differ in bits 3 and 4: fixed-order butterfly over the 4 position sub-indices
+    if (a.want_bias && blockIdx.x == 0) {        // (CTA-uniform)
+      // lanes sharing a chunk differ in bits 3 and 4: fixed-order butterfly over the 4 position sub-indices; with
+      // two warps per block the halves meet in shared memory and are added in half order
+      if (do_bias) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float t = bsum[j];
-        t += __shfl_xor_sync(0xffffffffu, t, 8);
-        t += __shfl_xor_sync(0xffffffffu, t, 16);
-        const int n = nbase + chunk * 4 + j;
-        if (psub == 0 && n < g.Cd) part[Ktot * g.Cd + n] = t;
+        for (int j = 0; j < 4; ++j) {
+          float t = bsum[j];
+          t += __shfl_xor_sync(0xffffffffu, t, 8);
+          t += __shfl_xor_sync(0xffffffffu, t, 16);
+          if (psub == 0) s_bias[blk][half][chunk * 4 + j] = t;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory");
+      if (do_bias && half == 0 && psub == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = nbase + chunk * 4 + j;
+          float t = s_bias[blk][0][chunk * 4 + j];
+          if (PH == 2) t += s_bias[blk][1][chunk * 4 + j];
+          if (n < g.Cd) part[Ktot * g.Cd + n] = t;
+        }
       }
     }
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    // TMEM lane = accumulator row = (row-block blk, channel lane); warps w and w+4 split the columns
-    const uint32_t taddr = tmem_base + ((uint32_t)(blk * 32) << 16);
-    const int64_t krow = (int64_t)tap * g.Cs + cb * 32 + lane;    // row of dW this thread owns
-    constexpr int CHALF = BN / 2;
-    const int cbeg = (warp >> 2) * CHALF;
+    // TMEM lane = accumulator row = (row-block q, channel lane), q = warp % 4 (a warp reaches lane quadrant
+    // warp % 4 only); the PW / 4 warps of a quadrant split the columns
+    const int q = warp & 3;
+    const int rb_e = rb0 + q;
+    const bool rbe_ok = rb_e < RB;
+    int tap_e = 0, cb_e = 0;
+    if (rbe_ok) { tap_e = rb_e / KC; cb_e = rb_e - tap_e * KC; }
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int64_t krow = (int64_t)tap_e * g.Cs + cb_e * 32 + lane;    // row of dW this thread owns
+    constexpr int CSL = BN / (PW / 4);
+    const int cbeg = (warp >> 2) * CSL;
 #pragma unroll 1
-    for (int c0 = cbeg; c0 < cbeg + CHALF; c0 += 16) {
+    for (int c0 = cbeg; c0 < cbeg + CSL; c0 += 16) {
       float acc[16];
       tmem_ld16(taddr + (uint32_t)c0, acc);
-      if (rb_ok && cb * 32 + lane < g.Cs) {
+      if (rbe_ok && cb_e * 32 + lane < g.Cs) {
         if (n0 + c0 + 16 <= g.Cd && (g.Cd & 3) == 0) {
           // (the workspace is 256-byte aligned and every partial slab is a multiple of Cd floats long)
           float* out = part + krow * g.Cd + n0 + c0;
@@ -1687,7 +1716,7 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
                         (2 * ST_ + 1) * 8 + 16;                                                                 \
     cudaFuncSetAttribute(conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_>,                                          \
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                               \
-    conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_><<<grid, UMF_THREADS, smem, st>>>(a);                           \
+    conv_wgrad_umma_kernel<BN_, SPLIT_, ST_, X_><<<grid, (BN_ == 128 ? 16 : 8) * 32 + 32, smem, st>>>(a);       \
   } while (0)
 #define LAUNCH_WG(BN_, SPLIT_, ST_)                                        \
   do {                                                                     \
