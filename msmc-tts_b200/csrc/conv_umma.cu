@@ -82,8 +82,20 @@ constexpr int UMF_THREADS = UMF_PRODUCERS + 32;  // + the MMA warp
 
 constexpr int UM_MAX_PHASE_TAPS = 256;
 
+// Producer / epilogue warps: 8, or 16 for the one-CTA-per-SM configuration (BN = 128, three stages): with 9 warps
+// on the SM every issue waited on a load or a dependent result and the tensor pipe idled (same finding as in the
+// weight-gradient kernel); 16 warps take two rows per thread and stage instead of four.
+template <int BN, int STAGES>
+struct UmmaFwdCfg {
+  static constexpr int PW = (BN == 128 && STAGES == 3) ? 16 : 8;
+  static constexpr int RPT = UM_BM / (PW * 4);     // rows per thread and stage: 4 or 2
+};
 template <int BN, bool SPLIT, int STAGES, int XFC, bool TRANSPOSED>
-__global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_kernel(const UmmaArgs a) {
+__global__ void __launch_bounds__(UmmaFwdCfg<BN, STAGES>::PW * 32 + 32, (STAGES == 2 ? 2 : 1))
+conv_umma_kernel(const UmmaArgs a) {
+  constexpr int PW = UmmaFwdCfg<BN, STAGES>::PW;
+  constexpr int RPT = UmmaFwdCfg<BN, STAGES>::RPT;
+  constexpr int RSTEP = PW * 4;                // row slots per pass: a warp instruction covers 4 rows
   const msmc_conv_geom& g = a.g;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: A stages (16 KB per plane), B stages (BN*128 B per plane), barriers, tmem slot
@@ -149,11 +161,11 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
     T = s_ntaps;
   }
   const int n_k = T * KC;
-  constexpr int MMA_WARP = UMF_PRODUCERS / 32;
+  constexpr int MMA_WARP = PW;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], UMF_PRODUCERS / 32 + 1);   // one arrival per producer warp + 1 arrive.expect_tx (weights)
+      mbar_init(&full_bar[s], PW + 1);   // one arrival per producer warp + 1 arrive.expect_tx (weights)
       mbar_init(&empty_bar[s], 1);                  // one tcgen05.commit
     }
     mbar_init(accum_bar, 1);
@@ -178,10 +190,10 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
     const int chunk = tid & 7;
     const int rsub = tid >> 3;                 // 0..31
     const int r8 = rsub & 7;                   // (row & 7) is the same for all rows of this thread
-    int pixb[4], hs0[4], ws0[4];               // batch pixel base / top-left source coordinate of each row
+    int pixb[RPT], hs0[RPT], ws0[RPT];               // batch pixel base / top-left source coordinate of each row
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t m = m0 + rsub + 32 * i;
+    for (int i = 0; i < RPT; ++i) {
+      const int64_t m = m0 + rsub + RSTEP * i;
       if (m < M) {
         const int b = (int)(m / ((int64_t)Hp * Wp));
         const int rem = (int)(m % ((int64_t)Hp * Wp));
@@ -195,16 +207,16 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
     }
     constexpr bool NEED_AUX = (XFC == XFC_GENERIC);
     const bool need_aux = NEED_AUX && xf_needs_aux(g.src_xf);
-    float4 v0[4], u0[4], v1[4], u1[4];          // two stages of loads in flight (prefetch distance 2)
+    float4 v0[RPT], u0[RPT], v1[RPT], u1[RPT];          // two stages of loads in flight (prefetch distance 2)
     int kc_n = 0, kh_n = 0, kw_n = 0, ti_n = 0;   // (chunk, tap) of the NEXT stage to gather
     if (TRANSPOSED && T > 0) { kh_n = s_tap_kh[0]; kw_n = s_tap_kw[0]; }
 
     // raw global loads only (no dependent math), so they stay in flight across the barrier round-trips
-    auto gather = [&](float4 (&v)[4], float4 (&u)[4]) {
+    auto gather = [&](float4 (&v)[RPT], float4 (&u)[RPT]) {
       const int coff = kc_n * UM_BK + chunk * 4;
       const int dh = kh_n * g.dh, dw = kw_n * g.dw;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < RPT; ++i) {
         int hs, ws;
         bool ok = pixb[i] >= 0;
         if (TRANSPOSED) {
@@ -246,7 +258,7 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
     int s = 0;
     uint32_t ph = 0;
     const uint32_t dst_off = (uint32_t)(rsub >> 3) * 1024u + (uint32_t)r8 * 128u + (uint32_t)((chunk ^ r8) << 4);
-    auto produce = [&](int ks, float4 (&v)[4], float4 (&u)[4]) {
+    auto produce = [&](int ks, float4 (&v)[RPT], float4 (&u)[RPT]) {
       mbar_wait(&empty_bar[s], ph ^ 1u);
       if (tid == 0) {
         mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
@@ -260,9 +272,9 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
       }
       uint8_t* dstbase = sA + s * A_BYTES + dst_off;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < RPT; ++i) {
         const float4 x = xf4<XFC>(g, v[i], NEED_AUX ? u[i] : make_float4(0.f, 0.f, 0.f, 0.f));
-        uint8_t* d = dstbase + i * 4096;        // rows advance by 32 -> four 1 KB swizzle atoms
+        uint8_t* d = dstbase + i * (RSTEP * 128);   // rows advance by RSTEP -> RSTEP / 8 one-KB swizzle atoms
         if (SPLIT) {
           const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
           *reinterpret_cast<float4*>(d) = hi;
@@ -298,7 +310,7 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
       // a phase without taps still owes bias / zeros to its destination rows
       if (row_ok) {
         const int n0z = n_tile * BN;
-        for (int j = (warp >> 2) * (BN / 2); j < (warp >> 2) * (BN / 2) + BN / 2; ++j) {
+        for (int j = (warp >> 2) * (BN / (PW / 4)); j < (warp >> 2) * (BN / (PW / 4)) + BN / (PW / 4); ++j) {
           const int n = n0z + j;
           if (n < g.Cd) {
             float x = a.bias ? __ldg(a.bias + n) : 0.f;
@@ -315,7 +327,7 @@ __global__ void __launch_bounds__(UMF_THREADS, (STAGES == 2 ? 2 : 1)) conv_umma_
     const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
     const int n0 = n_tile * BN;
     const bool dneed_aux = xf_needs_aux(g.dst_xf);
-    constexpr int CHALF = BN / 2;
+    constexpr int CHALF = BN / (PW / 4);         // the PW / 4 warps of a TMEM lane quadrant split the columns
     const int cbeg = (warp >> 2) * CHALF;
 #pragma unroll 1
     for (int c0 = cbeg; c0 < cbeg + CHALF; c0 += 16) {
@@ -468,8 +480,18 @@ struct ReuseArgs {
 };
 
 
+// Producer / epilogue warps: 8, or 16 for the one-CTA-per-SM configuration (BN = 128, two operand stages).
+template <int BN, int NA>
+struct ReuseCfg {
+  static constexpr int PW = (BN == 128 && NA == 2) ? 16 : 8;
+  static constexpr int THREADS = PW * 32 + 64;         // + MMA warp + weight-loader warp
+};
 template <int BN, bool SPLIT, int NA, int NBS, int XFC>
-__global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse_kernel(const ReuseArgs a) {
+__global__ void __launch_bounds__(ReuseCfg<BN, NA>::THREADS, (NA == 1 ? 2 : 1))
+conv_umma_reuse_kernel(const ReuseArgs a) {
+  constexpr int PW = ReuseCfg<BN, NA>::PW;
+  constexpr int RSTEP = PW * 4;                  // row slots per pass (a warp instruction covers 4 rows)
+  constexpr int RPT = RU_ROWS / RSTEP;           // rows per thread and chunk: 6 or 3
   const msmc_conv_geom& g = a.g;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -499,10 +521,10 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
   const int kc_beg = (KC * ks) / KS, kc_end = (KC * (ks + 1)) / KS;
   const int T = a.n_taps;
   const int r_in = UM_BM + (T - 1) * a.tap_stride;      // rows staged per chunk (<= RU_ROWS)
-  constexpr int MMA_WARP = RU_PRODUCERS / 32;   // warp MMA_WARP + 1 streams the weight tiles
+  constexpr int MMA_WARP = PW;                  // warp MMA_WARP + 1 streams the weight tiles
 
   if (tid == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&fa[i], RU_PRODUCERS / 32); mbar_init(&ea[i], 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&fa[i], PW); mbar_init(&ea[i], 1); }
     for (int i = 0; i < NBS; ++i) { mbar_init(&fb[i], 1); mbar_init(&eb[i], 1); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -521,17 +543,17 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
   if (warp < MMA_WARP) {
     // ================================= operand producers =================================
     const int chunk = tid & 7;
-    const int rsub = tid >> 3;                 // 0..31; rows rsub + 32*i, i = 0..5
+    const int rsub = tid >> 3;                 // 0..RSTEP-1; rows rsub + RSTEP*i, i = 0..RPT-1
     const int r8 = rsub & 7;
     constexpr bool NEED_AUX = (XFC == XFC_GENERIC);
     const bool need_aux = NEED_AUX && xf_needs_aux(g.src_xf);
     const int64_t pix0 = (int64_t)b * a.Ls;
-    float4 v[6], u[6];
+    float4 v[RPT], u[RPT];
     auto gather = [&](int kc) {
       const int coff = kc * UM_BK + chunk * 4;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int r = rsub + 32 * i;
+      for (int i = 0; i < RPT; ++i) {
+        const int r = rsub + RSTEP * i;
         const int p = l0 - a.pad_rows + r;               // source pixel inside this batch element
         if (r < r_in && (unsigned)p < (unsigned)a.Ls && coff < g.Cs) {
           v[i] = __ldg(reinterpret_cast<const float4*>(a.src + (pix0 + p) * g.ld_src + coff));
@@ -551,10 +573,10 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
       mbar_wait(&ea[sa], pa ^ 1u);
       uint8_t* dstbase = sA + sa * A_BYTES + dst_off;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        if (rsub + 32 * i < r_in) {
+      for (int i = 0; i < RPT; ++i) {
+        if (rsub + RSTEP * i < r_in) {
           const float4 x = xf4<XFC>(g, v[i], NEED_AUX ? u[i] : make_float4(0.f, 0.f, 0.f, 0.f));
-          uint8_t* d = dstbase + i * 4096;
+          uint8_t* d = dstbase + i * (RSTEP * 128);
           if (SPLIT) {
             const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
             *reinterpret_cast<float4*>(d) = hi;
@@ -632,7 +654,7 @@ __global__ void __launch_bounds__(RU_THREADS, (NA == 1 ? 2 : 1)) conv_umma_reuse
   // layout per partial: [column][128 rows] fp32 -- a warp's 32 rows are one 128-byte line on both sides
   const int lane_grp = warp & 3;
   const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-  constexpr int CHALF = BN / 2;
+  constexpr int CHALF = BN / (PW / 4);           // the PW / 4 warps of a TMEM lane quadrant split the columns
   const int cbeg = (warp >> 2) * CHALF;
   const int erow = lane_grp * 32 + (tid & 31);      // accumulator row of this thread (epilogue warps)
   if (KS > 1) {
@@ -1520,11 +1542,11 @@ extern "C" int msmc_conv_forward_umma(const msmc_conv_geom* gp, const float* src
     if (g.transposed) {                                                                                          \
       cudaFuncSetAttribute(conv_umma_kernel<BN_, SPLIT_, ST_, X_, true>,                                         \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              \
-      conv_umma_kernel<BN_, SPLIT_, ST_, X_, true><<<grid, UMF_THREADS, smem, st>>>(a);                          \
+      conv_umma_kernel<BN_, SPLIT_, ST_, X_, true><<<grid, UmmaFwdCfg<BN_, ST_>::PW * 32 + 32, smem, st>>>(a);  \
     } else {                                                                                                     \
       cudaFuncSetAttribute(conv_umma_kernel<BN_, SPLIT_, ST_, X_, false>,                                        \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              \
-      conv_umma_kernel<BN_, SPLIT_, ST_, X_, false><<<grid, UMF_THREADS, smem, st>>>(a);                         \
+      conv_umma_kernel<BN_, SPLIT_, ST_, X_, false><<<grid, UmmaFwdCfg<BN_, ST_>::PW * 32 + 32, smem, st>>>(a); \
     }                                                                                                            \
   } while (0)
 #define LAUNCH_UMMA(BN_, SPLIT_, ST_)                                \
@@ -1820,7 +1842,7 @@ extern "C" int msmc_conv_forward_umma_reuse(const msmc_conv_geom* gp, const floa
     cudaFuncSetAttribute(conv_umma_reuse_kernel<BN_, SPLIT_, NA_, NB_, X_>,                                       \
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                 \
     cudaLaunchConfig_t cfg = {};                                                                                  \
-    cfg.gridDim = grid; cfg.blockDim = dim3(RU_THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;      \
+    cfg.gridDim = grid; cfg.blockDim = dim3(ReuseCfg<BN_, NA_>::THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;      \
     cudaLaunchAttribute attr[1];                                                                                  \
     attr[0].id = cudaLaunchAttributeClusterDimension;                                                             \
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)KS;          \
