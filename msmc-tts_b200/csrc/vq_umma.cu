@@ -187,23 +187,34 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
   __syncthreads();        // barriers initialised: the staging warps may signal a_full during the prologue
   // A operand of one tile: 128 rows x 16 sixteen-byte chunks; consecutive threads read consecutive chunks of a row
   // (256 B per row); hi / lo planes, K-major SWIZZLE_128B
-  auto stage_tile = [&](int tile, int st) {
+  // `nthr` threads (st = 0 .. nthr-1) share the tile; eight loads are issued before the first is consumed (the
+  // compiler did not unroll this loop inside the lambda: 32 dependent round trips made a single-tile launch 10 us
+  // longer than the pipelined per-tile period)
+  auto stage_rows = [&](int tile, int st, int nthr) {
     const int row0 = tile * VU_ROWS;
-#pragma unroll 8
-    for (int i = 0; i < (VU_ROWS * 16) / 64; ++i) {
-      const int e = st + 64 * i;
-      const int r = e >> 4, c_all = e & 15;
-      const int half = c_all >> 3, chunk = c_all & 7;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + r < n_rows)
-        x = __ldg(reinterpret_cast<const float4*>(z + (int64_t)(row0 + r) * ld_z + h * VU_DIM + c_all * 4));
-      const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
-      uint8_t* d = sA + (half * 2) * A_PLANE + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
-                   (uint32_t)((chunk ^ (r & 7)) << 4);
-      *reinterpret_cast<float4*>(d) = hi;
-      *reinterpret_cast<float4*>(d + A_PLANE) = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+    for (int e0 = st; e0 < VU_ROWS * 16; e0 += 8 * nthr) {
+      float4 x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = e0 + j * nthr;
+        const int r = e >> 4, c_all = e & 15;
+        x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < n_rows)
+          x[j] = __ldg(reinterpret_cast<const float4*>(z + (int64_t)(row0 + r) * ld_z + h * VU_DIM + c_all * 4));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = e0 + j * nthr;
+        const int r = e >> 4, c_all = e & 15;
+        const int half = c_all >> 3, chunk = c_all & 7;
+        const float4 hi = make_float4(tf32_hi(x[j].x), tf32_hi(x[j].y), tf32_hi(x[j].z), tf32_hi(x[j].w));
+        uint8_t* d = sA + (half * 2) * A_PLANE + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+                     (uint32_t)((chunk ^ (r & 7)) << 4);
+        *reinterpret_cast<float4*>(d) = hi;
+        *reinterpret_cast<float4*>(d + A_PLANE) =
+            make_float4(x[j].x - hi.x, x[j].y - hi.y, x[j].z - hi.z, x[j].w - hi.w);
+      }
     }
-    publish_and_arrive_warp(a_full);
   };
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -255,8 +266,12 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
       m = warp_max(m);
       if (lane == 0) ee_max[0] = m;
     }
-  } else if (warp < VU_EPI / 32 + 2) {
-    stage_tile(blockIdx.x, tid - VU_EPI);      // the first tile's rows arrive while the codebook is being staged
+  } else if (warp < MMA_WARP) {
+    // the first tile's rows arrive while the codebook is being staged: all four staging / head-sum warps take part
+    stage_rows(blockIdx.x, tid - VU_EPI, VU_STAGERS);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("bar.sync 3, %0;" ::"n"(VU_STAGERS) : "memory");
+    if (warp < VU_EPI / 32 + 2 && lane == 0) mbar_arrive(a_full);      // (count 2: the two staging warps)
   }
   tc_fence_before();
   __syncthreads();
@@ -430,7 +445,8 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
     uint32_t it = 1;                                     // (tile 0 was staged during the prologue)
     for (int tile = blockIdx.x + gridDim.x; tile < n_tiles; tile += gridDim.x, ++it) {
       mbar_wait(a_free, (it - 1) & 1u);                    // the previous tile's MMAs have read the stage
-      stage_tile(tile, st);
+      stage_rows(tile, st, 64);
+      publish_and_arrive_warp(a_full);
     }
   } else if (warp < MMA_WARP) {
     // ================================ head sum of the commitment term ================================
