@@ -77,6 +77,9 @@ __device__ __forceinline__ float4 xf4(const msmc_conv_geom& g, float4 x, float4 
   return x;
 }
 
+// fewest source channels the tensor-core kernels take: below 32 the single 32-channel chunk is ragged (zero-filled
+// in the operand tile and the weight image), which wastes MMA width the CUDA-core fallbacks do not have to spare
+constexpr int UM_MIN_CS = 8;
 constexpr int UMF_PRODUCERS = 256;             // 8 producer / epilogue warps
 constexpr int UMF_THREADS = UMF_PRODUCERS + 32;  // + the MMA warp
 
@@ -1517,7 +1520,7 @@ extern "C" int msmc_conv_forward_umma(const msmc_conv_geom* gp, const float* src
   MSMC_REQUIRE(gp && src && wimg && dst);
   const msmc_conv_geom& g = *gp;
   MSMC_REQUIRE(!(g.transposed && g.pad_reflect));
-  MSMC_REQUIRE(g.Cs % 4 == 0 && g.Cs >= UM_BK && g.ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  MSMC_REQUIRE(g.Cs % 4 == 0 && g.Cs >= UM_MIN_CS && g.ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
   MSMC_REQUIRE(!xf_needs_aux(g.src_xf) ||
                (src_aux && g.ld_saux % 4 == 0 && (reinterpret_cast<uintptr_t>(src_aux) & 15) == 0));
   MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || dst_aux);
@@ -1641,7 +1644,7 @@ bool wgrad_reuse_plan(const msmc_conv_geom& g, bool split, WgradReusePlan* p) {
 }  // namespace
 
 extern "C" int64_t msmc_conv_wgrad_umma_workspace(const msmc_conv_geom* gp) {
-  if (!gp || gp->Cs % 4 != 0 || gp->Cs < 32) return -1;
+  if (!gp || gp->Cs % 4 != 0 || gp->Cs < UM_MIN_CS) return -1;
   const msmc_conv_geom& g = *gp;
   {
     WgradReusePlan rp;
@@ -1657,7 +1660,7 @@ extern "C" int msmc_conv_wgrad_umma(const msmc_conv_geom* gp, const float* src, 
                                     float* workspace, int64_t workspace_bytes, int32_t split, void* stream) {
   MSMC_REQUIRE(gp && src && gout && dw && workspace);
   const msmc_conv_geom& g = *gp;
-  MSMC_REQUIRE(!g.transposed && g.Cs % 4 == 0 && g.Cs >= 32 && g.ld_src % 4 == 0 &&
+  MSMC_REQUIRE(!g.transposed && g.Cs % 4 == 0 && g.Cs >= UM_MIN_CS && g.ld_src % 4 == 0 &&
                (reinterpret_cast<uintptr_t>(src) & 15) == 0);
   MSMC_REQUIRE(!xf_needs_aux(g.src_xf) ||
                (src_aux && g.ld_saux % 4 == 0 && (reinterpret_cast<uintptr_t>(src_aux) & 15) == 0));
@@ -1780,7 +1783,7 @@ bool reuse_eligible(const msmc_conv_geom& g, int* tap_stride, int* n_taps, int* 
 
 extern "C" int msmc_conv_reuse_eligible(const msmc_conv_geom* gp) {
   int a, b, c;
-  return gp && gp->Cs % 4 == 0 && gp->Cs >= UM_BK && reuse_eligible(*gp, &a, &b, &c) ? 1 : 0;
+  return gp && gp->Cs % 4 == 0 && gp->Cs >= UM_MIN_CS && reuse_eligible(*gp, &a, &b, &c) ? 1 : 0;
 }
 
 extern "C" int msmc_conv_forward_umma_reuse(const msmc_conv_geom* gp, const float* src, const float* src_aux,
@@ -1791,7 +1794,7 @@ extern "C" int msmc_conv_forward_umma_reuse(const msmc_conv_geom* gp, const floa
   const msmc_conv_geom& g = *gp;
   ReuseArgs a;
   MSMC_REQUIRE(reuse_eligible(g, &a.tap_stride, &a.n_taps, &a.pad_rows));
-  MSMC_REQUIRE(g.Cs % 4 == 0 && g.Cs >= UM_BK && g.ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  MSMC_REQUIRE(g.Cs % 4 == 0 && g.Cs >= UM_MIN_CS && g.ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0);
   MSMC_REQUIRE(!xf_needs_aux(g.src_xf) ||
                (src_aux && g.ld_saux % 4 == 0 && (reinterpret_cast<uintptr_t>(src_aux) & 15) == 0));
   MSMC_REQUIRE(!xf_needs_aux(g.dst_xf) || dst_aux);

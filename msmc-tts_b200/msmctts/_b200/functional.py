@@ -15,6 +15,11 @@ from . import lib as L
 #   "fp32"             CUDA-core FMA kernels only
 CONV_MATH = os.environ.get("MSMC_CONV_MATH", "3xtf32")
 UMMA_MIN_ROWS = 256
+# fewest source channels routed to the tensor-core conv kernels.  The kernels take >= 8 (csrc UM_MIN_CS: one ragged,
+# zero-filled 32-channel chunk) and are parity-tested there, but measured on the train step the CUDA-core kernels win
+# below 32: 37.4 ms/step at 32, 38.1 at 16, 40.1 at 8 (profiles/README.md) -- those layers are all position tiles
+# and no reduction, so the per-tile fixed cost of the tensor-core kernels dominates
+UMMA_MIN_CS = int(os.environ.get("MSMC_UMMA_MIN_CS", "32"))
 USE_TAP_REUSE = os.environ.get("MSMC_TAP_REUSE", "1") != "0"
 # VQ search kernel choice: "auto" = the two-phase tensor-core kernel (csrc/vq_umma.cu, bit-identical results) from
 # VQ_UMMA_MIN_ROWS rows on -- below that a launch is one row tile per CTA and the CUDA-core cluster kernel's shorter
@@ -136,7 +141,7 @@ def flush_deferred(jobs, key):
 
 
 def _umma_ok(src, ld_src, w, wstr_gemm, KH, KW, Cs, Cd_gemm, rows, saux, ld_saux):
-    if CONV_MATH == "fp32" or Cs % 4 != 0 or Cs < 32 or rows < UMMA_MIN_ROWS:      # a ragged last 32-channel chunk is fine
+    if CONV_MATH == "fp32" or Cs % 4 != 0 or Cs < UMMA_MIN_CS or rows < UMMA_MIN_ROWS:      # a ragged last 32-channel chunk is fine
         return False
     if not w.is_contiguous() or w.numel() != KH * KW * wstr_gemm[0] * wstr_gemm[1]:
         return False
@@ -223,7 +228,7 @@ def _launch_wgrad(src, gout, dw, wstr, dbias, KH, KW, sh, sw, dh, dw_, ph, pw, r
         meta = {"flops": 2.0 * B * Hd * Wd * KH * KW * Cs * Cd,
                 "bytes": 4.0 * (src.numel() + gout.numel() + KH * KW * Cs * Cd),
                 "shape": "wgrad B%d %dx%d C%d->%d k%dx%d" % (B, Hs, Ws, Cs, Cd, KH, KW)}
-    use_umma = (CONV_MATH != "fp32" and Cs % 4 == 0 and Cs >= 32 and ld_src % 4 == 0 and src.data_ptr() % 16 == 0
+    use_umma = (CONV_MATH != "fp32" and Cs % 4 == 0 and Cs >= UMMA_MIN_CS and ld_src % 4 == 0 and src.data_ptr() % 16 == 0
                 and B * Hd * Wd >= UMMA_MIN_ROWS
                 and (saux is None or (g.ld_saux % 4 == 0 and saux.data_ptr() % 16 == 0)))
     if use_umma:
@@ -434,7 +439,7 @@ def linear_cl(x, weight, bias=None, residual=None, post="none", pre_slope=None, 
     lead = x.shape[:-1]
     x4 = x.reshape(-1, 1, 1, Ci)
     r4 = residual.reshape(-1, 1, 1, Co) if residual is not None else None
-    umma = CONV_MATH != "fp32" and Ci % 4 == 0 and Ci >= 32 and x4.shape[0] >= UMMA_MIN_ROWS and weight.requires_grad
+    umma = CONV_MATH != "fp32" and Ci % 4 == 0 and Ci >= UMMA_MIN_CS and x4.shape[0] >= UMMA_MIN_ROWS and weight.requires_grad
     if owner is not None:
         owner.__dict__["_msmc_lin_umma"] = bool(umma)
     if umma:

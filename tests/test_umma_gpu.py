@@ -42,6 +42,11 @@ CASES = [
     ("AM downsampler Cs600 k9", 2, 1, 300, 600, 600, 1, 9, (1, 1), (1, 1), (0, 4), False, None, "none", False),
     ("AM linear 1456->600", 1, 1, 480, 1456, 600, 1, 1, (1, 1), (1, 1), (0, 0), False, None, "none", False),
     ("ragged Cs40 strided 2-D", 2, 30, 20, 40, 48, 3, 3, (2, 1), (1, 1), (1, 1), False, 0.2, "none", False),
+    # fewer than 32 source channels (second layers of the MRD / MPD stacks): one ragged chunk
+    ("mrd 3x3 reflect s(1,2) Cs16", 2, 51, 60, 16, 32, 3, 3, (1, 2), (1, 1), (1, 1), True, None, "lrelu", False),
+    ("mpd (5,1) s(3,1) Cs16", 2, 200, 7, 16, 64, 5, 1, (3, 1), (1, 1), (2, 0), False, 0.2, "none", False),
+    ("mrd 3x3 reflect s1 Cs8", 2, 60, 40, 8, 16, 3, 3, (1, 1), (1, 1), (1, 1), True, None, "lrelu", False),
+    ("k3 Cs16 Cd16 1-D", 2, 1, 700, 16, 16, 1, 3, (1, 1), (1, 1), (0, 1), False, 0.1, "none", True),
 ]
 
 
@@ -105,6 +110,7 @@ def _run_case(case, tol, cmp=None):
 def test_conv_umma_3xtf32(case, monkeypatch):
     from msmctts._b200 import functional as Fn
     monkeypatch.setattr(Fn, "CONV_MATH", "3xtf32")
+    monkeypatch.setattr(Fn, "UMMA_MIN_CS", 8)      # (the default policy keeps Cs < 32 on the CUDA-core kernels)
     # 2e-5 of the tensor max up to reductions of ~1.5k terms (the GAN step's longest is 3 x 1024).  The hi / lo split
     # TRUNCATES (hi = top 19 bits, the tensor core truncates lo to TF32 again), so every partial product carries a
     # relative error of ~2^-22 with the SIGN OF THE PRODUCT: it does not average out, the bound grows with the
