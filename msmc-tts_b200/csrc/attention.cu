@@ -7,6 +7,7 @@
 //       [h*3D, h*3D+D) = q, [.. +D, +2D) = k, [.. +2D, +3D) = v   (transformer.py:253-260)
 // out : (B, t, n_head*D) with head-major columns (transformer.py:270-272)
 #include "common.cuh"
+#include <cstdlib>
 
 namespace msmc {
 namespace {
@@ -367,11 +368,40 @@ extern "C" int msmc_attention_bwd(const float* qkv, const int32_t* lengths, cons
   cudaFuncSetAttribute(attention_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
   cudaFuncSetAttribute(attention_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv);
   dim3 gq(ceil_div(t, TQ), B * n_head), gk(ceil_div(t, TK), B * n_head);
-  attention_bwd_dq_kernel<<<gq, 256, smem_q, st>>>(qkv, lengths, out, lse, gout, gqkv, B, t, n_head,
-                                                   inv_temperature, drop_p, seed, call_salt);
-  MSMC_CHECK_LAUNCH();
+  // dQ and dK/dV are independent (they write disjoint columns of gqkv) and neither fills the GPU evenly on its own
+  // (256 CTAs: two uneven waves at one CTA per SM for dK/dV): dQ is forked onto a helper stream and joined again, so
+  // the block scheduler packs the CTAs of both.  Event fork / join is capturable in CUDA graphs.  One helper stream
+  // and event pair per calling thread (the trainer drives the encoder / decoder chain from one thread, one stream).
+  struct Fork { cudaStream_t s2 = nullptr; cudaEvent_t e1 = nullptr, e2 = nullptr; int dev = -1; };
+  static thread_local Fork fk;
+  static const bool use_fork = [] { const char* e = getenv("MSMC_ATTN_BWD_FORK"); return e ? atoi(e) != 0 : false; }();   // (off until measured)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (use_fork && fk.dev != dev) {
+    fk = Fork();
+    if (cudaStreamCreateWithFlags(&fk.s2, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&fk.e1, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&fk.e2, cudaEventDisableTiming) == cudaSuccess)
+      fk.dev = dev;
+    else
+      cudaGetLastError();
+  }
+  const bool fork = use_fork && fk.dev == dev;
+  cudaStream_t sq = st;
+  if (fork) {
+    if (cudaEventRecord(fk.e1, st) != cudaSuccess || cudaStreamWaitEvent(fk.s2, fk.e1, 0) != cudaSuccess)
+      return MSMC_ERR_LAUNCH;
+    sq = fk.s2;
+  }
   attention_bwd_dkv_kernel<<<gk, 256, smem_kv, st>>>(qkv, lengths, out, lse, gout, gqkv, B, t, n_head,
                                                      inv_temperature, drop_p, seed, call_salt);
   MSMC_CHECK_LAUNCH();
+  attention_bwd_dq_kernel<<<gq, 256, smem_q, sq>>>(qkv, lengths, out, lse, gout, gqkv, B, t, n_head,
+                                                   inv_temperature, drop_p, seed, call_salt);
+  MSMC_CHECK_LAUNCH();
+  if (fork) {
+    if (cudaEventRecord(fk.e2, fk.s2) != cudaSuccess || cudaStreamWaitEvent(st, fk.e2, 0) != cudaSuccess)
+      return MSMC_ERR_LAUNCH;
+  }
   return MSMC_OK;
 }
