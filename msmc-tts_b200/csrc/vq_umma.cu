@@ -227,17 +227,31 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
     // sectors along the codewords of one dim (the codebook is dim-major), the 16-byte shared-memory stores of a
     // quarter warp hit the 8 distinct chunk positions c ^ (k & 7) of 8 consecutive rows: conflict-free
     {
+      // (K / 8) * 4 items over 8 warps, 8 items = 32 loads in flight per thread and round trip: the prologue is a
+      // chain of dependent L2 / DRAM round trips and a single-tile launch is mostly prologue
       const int kk = lane & 7, dc = lane >> 3;
-#pragma unroll 4
-      for (int item = warp; item < (K / 8) * 4; item += VU_EPI / 32) {
-        const int k = (item >> 2) * 8 + kk, c = (item & 3) * 4 + dc;      // codeword, 16-byte chunk of its 64 dims
-        float xv[4];
+      constexpr int ITEMS = (K / 8) * 4 / (VU_EPI / 32);      // items per warp: 4, 8 or 16
+      constexpr int BATCH = ITEMS < 8 ? ITEMS : 8;
+#pragma unroll 1
+      for (int i0 = 0; i0 < ITEMS; i0 += BATCH) {
+        float xv[BATCH][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) xv[j] = __ldg(e_h + (size_t)(c * 4 + j) * K + k);
-        const float4 hi = make_float4(tf32_hi(xv[0]), tf32_hi(xv[1]), tf32_hi(xv[2]), tf32_hi(xv[3]));
-        uint8_t* d = sB + ((c >> 3) * 2) * B_PLANE + (uint32_t)k * 128u + (uint32_t)((((c & 7) ^ k) & 7) << 4);
-        *reinterpret_cast<float4*>(d) = hi;
-        *reinterpret_cast<float4*>(d + B_PLANE) = make_float4(xv[0] - hi.x, xv[1] - hi.y, xv[2] - hi.z, xv[3] - hi.w);
+        for (int b = 0; b < BATCH; ++b) {
+          const int item = warp + (VU_EPI / 32) * (i0 + b);
+          const int k = (item >> 2) * 8 + kk, c = (item & 3) * 4 + dc;    // codeword, 16-byte chunk of its 64 dims
+#pragma unroll
+          for (int j = 0; j < 4; ++j) xv[b][j] = __ldg(e_h + (size_t)(c * 4 + j) * K + k);
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int item = warp + (VU_EPI / 32) * (i0 + b);
+          const int k = (item >> 2) * 8 + kk, c = (item & 3) * 4 + dc;
+          const float4 hi = make_float4(tf32_hi(xv[b][0]), tf32_hi(xv[b][1]), tf32_hi(xv[b][2]), tf32_hi(xv[b][3]));
+          uint8_t* d = sB + ((c >> 3) * 2) * B_PLANE + (uint32_t)k * 128u + (uint32_t)((((c & 7) ^ k) & 7) << 4);
+          *reinterpret_cast<float4*>(d) = hi;
+          *reinterpret_cast<float4*>(d + B_PLANE) =
+              make_float4(xv[b][0] - hi.x, xv[b][1] - hi.y, xv[b][2] - hi.z, xv[b][3] - hi.w);
+        }
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the planes are read by the async proxy (MMA)
