@@ -111,15 +111,27 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
   return v[0];
 }
 
-// the oracle's exact arithmetic for one (row, codeword): sequential fma over the dims, operands straight from global
-// memory (only the rare ambiguous rows come here)
-__device__ __noinline__ float exact_dist(const float* __restrict__ zrow, const float* __restrict__ e, int K, int k,
-                                         float eek) {
+// the oracle's exact arithmetic for one (row, codeword): sequential fma over the dims.  The row comes from global
+// memory (two L1 lines), the codeword from the resident planes (hi + lo is the exact fp32 element).  Inlined and
+// streaming: no register array, no call.
+template <int K>
+__device__ __forceinline__ float exact_dist(const float* __restrict__ zrow, const uint8_t* __restrict__ sB, int k,
+                                            float eek) {
+  constexpr int B_PLANE = K * 128;
   float zz = 0.f, dot = 0.f;
-  for (int d = 0; d < VU_DIM; ++d) {
-    const float zv = __ldg(zrow + d);
-    zz = fmaf(zv, zv, zz);
-    dot = fmaf(zv, __ldg(e + (size_t)d * K + k), dot);
+#pragma unroll 4
+  for (int c = 0; c < 16; ++c) {
+    const float4 zv = __ldg(reinterpret_cast<const float4*>(zrow) + c);
+    const uint8_t* a = sB + ((c >> 3) * 2) * B_PLANE + (uint32_t)k * 128u + (uint32_t)((((c & 7) ^ k) & 7) << 4);
+    const float4 hi = *reinterpret_cast<const float4*>(a);
+    const float4 lo = *reinterpret_cast<const float4*>(a + B_PLANE);
+    const float ev[4] = {hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w};
+    const float zc[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      zz = fmaf(zc[j], zc[j], zz);
+      dot = fmaf(zc[j], ev[j], dot);
+    }
   }
   return (zz - 2.f * dot) + eek;
 }
@@ -378,17 +390,31 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
         const float* zrow = z + (int64_t)min(row_w + lane, n_rows - 1) * ld_z + h * VU_DIM;
         float bd = INFINITY;
         int bk = 0x7fffffff;
-#pragma unroll 1
+        // pass 1 (whole warp, straight-line): candidate columns of this lane's row as a bit mask -- no divergence
+        // between the warp-collective TMEM loads; pass 2: the ambiguous lanes walk their few set bits in ascending
+        // order.  (This block costs ~23 k cycles when it runs, however the re-score is written -- measured with
+        // clock64; about one row in 8 000 is ambiguous, so nearly every launch at the training shape has one: that is
+        // the 18 vs 31 us of the single-tile launches.  Not understood yet)
+        uint32_t cand[K / 32];
+#pragma unroll
+        for (int w = 0; w < K / 32; ++w) cand[w] = 0u;
+#pragma unroll
         for (int c0 = 0; c0 < K; c0 += 16) {
           float acc[16];
           tmem_ld16(taddr + (uint32_t)c0, acc);
-          if (amb) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if ((zz - 2.f * acc[j]) + ee[c0 + j] <= thr) {
-                const float dk = exact_dist(zrow, e_h, K, c0 + j, ee[c0 + j]);
-                if (dk < bd) { bd = dk; bk = c0 + j; }
-              }
+          for (int j = 0; j < 16; ++j)
+            if ((zz - 2.f * acc[j]) + ee[c0 + j] <= thr) cand[c0 >> 5] |= 1u << ((c0 & 31) + j);
+        }
+        if (amb) {
+#pragma unroll
+          for (int w = 0; w < K / 32; ++w) {
+            uint32_t m = cand[w];
+            while (m) {
+              const int k = w * 32 + __ffs(m) - 1;
+              m &= m - 1;
+              const float dk = exact_dist<K>(zrow, sB, k, ee[k]);
+              if (dk < bd) { bd = dk; bk = k; }
             }
           }
         }
@@ -587,7 +613,8 @@ int launch_vq_umma(const float* z, int64_t ld_z, const float* embed, float* quan
     }
     max_clusters[n_heads] = std::min(nc, num_sms() / n_heads);
   }
-  const int n_clusters = std::max(1, std::min(ceil_div(n_rows, VU_ROWS), max_clusters[n_heads]));
+  int n_clusters = std::max(1, std::min(ceil_div(n_rows, VU_ROWS), max_clusters[n_heads]));
+  if (const char* e = getenv("MSMC_VQ_MAX_CLUSTERS")) n_clusters = std::max(1, std::min(n_clusters, atoi(e)));
   cfg.gridDim = dim3((unsigned)n_clusters, (unsigned)n_heads, 1);
   if (cudaLaunchKernelEx(&cfg, vq_search_umma_kernel<K>, z, ld_z, embed, quant_raw, quant_st, diff, idx, n_rows) !=
       cudaSuccess)
