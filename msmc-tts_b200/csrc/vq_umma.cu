@@ -390,32 +390,28 @@ vq_search_umma_kernel(const float* __restrict__ z, int64_t ld_z, const float* __
         const float* zrow = z + (int64_t)min(row_w + lane, n_rows - 1) * ld_z + h * VU_DIM;
         float bd = INFINITY;
         int bk = 0x7fffffff;
-        // pass 1 (whole warp, straight-line): candidate columns of this lane's row as a bit mask -- no divergence
-        // between the warp-collective TMEM loads; pass 2: the ambiguous lanes walk their few set bits in ascending
-        // order.  (This block costs ~23 k cycles when it runs, however the re-score is written -- measured with
-        // clock64; about one row in 8 000 is ambiguous, so nearly every launch at the training shape has one: that is
-        // the 18 vs 31 us of the single-tile launches.  Not understood yet)
-        uint32_t cand[K / 32];
+        // A SMALL LOOPED body (32 columns per iteration: two warp-collective TMEM loads, a 32-bit candidate mask,
+        // the exact re-score of its set bits in ascending order): this block runs about once per 8 000 row-heads, so
+        // its code is never in the instruction cache -- fully unrolled (1 300 instructions of straight-line code) it
+        // cost 22 - 25 k cycles of instruction fetch for ~5 k cycles of work, which is what separated the 18 us and
+        // the 31 us single-tile launches (profiles/r02_vq_small_probe.txt)
+#pragma unroll 1
+        for (int w = 0; w < K / 32; ++w) {
+          uint32_t m = 0u;
 #pragma unroll
-        for (int w = 0; w < K / 32; ++w) cand[w] = 0u;
+          for (int hf = 0; hf < 2; ++hf) {
+            float acc[16];
+            tmem_ld16(taddr + (uint32_t)(w * 32 + hf * 16), acc);
 #pragma unroll
-        for (int c0 = 0; c0 < K; c0 += 16) {
-          float acc[16];
-          tmem_ld16(taddr + (uint32_t)c0, acc);
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if ((zz - 2.f * acc[j]) + ee[c0 + j] <= thr) cand[c0 >> 5] |= 1u << ((c0 & 31) + j);
-        }
-        if (amb) {
-#pragma unroll
-          for (int w = 0; w < K / 32; ++w) {
-            uint32_t m = cand[w];
-            while (m) {
-              const int k = w * 32 + __ffs(m) - 1;
-              m &= m - 1;
-              const float dk = exact_dist<K>(zrow, sB, k, ee[k]);
-              if (dk < bd) { bd = dk; bk = k; }
-            }
+            for (int j = 0; j < 16; ++j)
+              if ((zz - 2.f * acc[j]) + ee[w * 32 + hf * 16 + j] <= thr) m |= 1u << (hf * 16 + j);
+          }
+          if (!amb) m = 0u;
+          while (m) {
+            const int k = w * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            const float dk = exact_dist<K>(zrow, sB, k, ee[k]);
+            if (dk < bd) { bd = dk; bk = k; }
           }
         }
         if (amb) best_k = ((unsigned)bk < (unsigned)K) ? bk : 0;     // no candidate at all (NaN row): index 0
